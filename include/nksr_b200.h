@@ -1,0 +1,187 @@
+/* nksr_b200 -- C-ABI of the B200-native NKSR reconstruction hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a cudaStream_t
+ * (passed as void*), performs NO allocation (the caller owns every buffer, normally torch
+ * tensors) and returns 0 or a negative NKSR_E* code.  Variable-size outputs are two-phase:
+ * a *_count / capacity call, the caller allocates, a *_fill call.
+ *
+ * The reference ships this path as the closed `nksr` wheel, so each group below cites the
+ * reference CALL SITE whose behaviour it replaces (paths relative to /root/reference).
+ * The reference-side binding is the ctypes shim in nksr_b200/_lib.py.
+ */
+#ifndef NKSR_B200_H
+#define NKSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NKSR_API __attribute__((visibility("default")))
+#else
+#define NKSR_API
+#endif
+
+#define NKSR_MAX_DEPTH 8
+#define NKSR_ROW_STRIDE 32 /* a kernel-row has 27 stencil slots, padded to one 128 B line */
+
+enum {
+  NKSR_OK = 0,
+  NKSR_E_INVALID = -1,   /* bad argument                                  */
+  NKSR_E_RANGE = -2,     /* coordinate outside the 2^19-voxel key range    */
+  NKSR_E_WORKSPACE = -3, /* workspace too small                            */
+  NKSR_E_CUDA = -4,      /* a CUDA call failed (cudaGetLastError)          */
+  NKSR_E_STRUCTURE = -5  /* hierarchy not parent-closed / table mismatch   */
+};
+
+/* Device view of a sparse voxel hierarchy (replaces nksr.SparseFeatureHierarchy internals;
+ * contract: models/nksr_net.py:57-62, models/loss.py:33-46). Level l has voxel size
+ * voxel_size*2^l; voxels of a level are sorted by 63-bit Morton key. */
+typedef struct {
+  int32_t depth;
+  float voxel_size;
+  int64_t n[NKSR_MAX_DEPTH];             /* voxels per level                         */
+  int64_t offset[NKSR_MAX_DEPTH];        /* first unknown of the level in alpha      */
+  const int64_t* keys[NKSR_MAX_DEPTH];   /* [n] sorted Morton keys                   */
+  const int32_t* parent[NKSR_MAX_DEPTH]; /* [n] index at level+1 (NULL at the top)   */
+  const int32_t* child8[NKSR_MAX_DEPTH]; /* [n][8] index at level-1, -1 (NULL at 0)  */
+  const int32_t* nbr27[NKSR_MAX_DEPTH];  /* [n][27] same-level neighbours, -1        */
+} nksr_svh_t;
+
+/* Per-level kernel features z_i (replaces features=feat.basis_features passed to
+ * nksr.fields.KernelField, models/nksr_net.py:91-96). */
+typedef struct {
+  int32_t channels; /* C: 1..32 */
+  const float* z[NKSR_MAX_DEPTH]; /* [n_l][C] */
+} nksr_feat_t;
+
+NKSR_API const char* nksr_version(void);
+NKSR_API const char* nksr_error_string(int code);
+
+/* ---- a1: SparseFeatureHierarchy.build_point_splatting (models/nksr_net.py:57-62) ---- */
+/* half-voxel Morton key of every point: morton(floor(x/(W/2)) + 2^20). status[0] |= 1 on range error */
+NKSR_API int nksr_point_half_keys(const float* xyz, int64_t n, float voxel_size, int64_t* keys,
+                         int32_t* status, void* stream);
+NKSR_API size_t nksr_sort_workspace_bytes(int64_t n, int pairs);
+NKSR_API int nksr_sort_keys(const int64_t* keys_in, int64_t* keys_out, int64_t n, void* ws,
+                   size_t ws_bytes, void* stream);
+NKSR_API int nksr_sort_pairs(const int64_t* keys_in, int64_t* keys_out, const int32_t* vals_in,
+                    int32_t* vals_out, int64_t n, void* ws, size_t ws_bytes, void* stream);
+NKSR_API size_t nksr_unique_workspace_bytes(int64_t n);
+/* out = unique(in >> shift) for sorted `in`; *count_out (device int64) = number written */
+NKSR_API int nksr_unique_sorted(const int64_t* in, int64_t n, int shift, int64_t* out,
+                       int64_t* count_out, void* ws, size_t ws_bytes, void* stream);
+/* 8 splat candidates (level-l voxel keys) per unique level-l half key */
+NKSR_API int nksr_splat_candidates(const int64_t* half_keys, int64_t n, int64_t* out8, void* stream);
+NKSR_API int nksr_parent_index(const int64_t* keys, int64_t n, const int64_t* keys_up, int64_t n_up,
+                      int32_t* parent, int32_t* status, void* stream);
+NKSR_API int nksr_child_table(const int64_t* keys, const int32_t* parent, int64_t n, int32_t* child8_up,
+                     int64_t n_up, void* stream);
+NKSR_API int nksr_nbr27_search(const int64_t* keys, int64_t n, int32_t* nbr27, void* stream);
+NKSR_API int nksr_nbr27_from_parent(const int64_t* keys, const int32_t* parent, int64_t n,
+                           const int32_t* nbr27_up, const int32_t* child8_up, int32_t* nbr27,
+                           void* stream);
+/* active_grid_coords() (models/loss.py:36): int32 ijk per voxel */
+NKSR_API int nksr_decode_ijk(const int64_t* keys, int64_t n, int level, int32_t* ijk, void* stream);
+/* containing voxel per level for M locations: base[l*M + m], -1 if inactive */
+NKSR_API int nksr_locate(const nksr_svh_t* svh, const float* xyz, int64_t m, int32_t* base, void* stream);
+/* first/last+1 sorted location of every level-l voxel: range[2*u], range[2*u+1] */
+NKSR_API int nksr_row_ranges(const int32_t* base_l, int64_t m, int32_t* range, int64_t n_l, void* stream);
+
+/* ---- a3: KernelField.solve* Gram assembly (models/nksr_net.py:100-112) ---- */
+/* kernel rows. mode 0: value rows  e[(l*M + m)*32 + s]            (position constraints)
+ *              mode 1: gradient rows e[((l*M + m)*3 + a)*32 + s]  (normal constraints)   */
+NKSR_API int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* xyz,
+                    const int32_t* base, int64_t m, int mode, int approx_kernel_grad, float* e,
+                    void* stream);
+/* structural row lengths of A: cnt[i] (same + coarser levels), cnt_down[i] (finer levels) */
+NKSR_API int nksr_gram_count(const nksr_svh_t* svh, int32_t* cnt, int32_t* cnt_down, void* stream);
+NKSR_API size_t nksr_scan_workspace_bytes(int64_t n);
+/* rowptr[0..n] (int64) = exclusive scan of cnt[i] + cnt_down[i] */
+NKSR_API int nksr_gram_rowptr(const int32_t* cnt, const int32_t* cnt_down, int64_t n, int64_t* rowptr,
+                     void* ws, size_t ws_bytes, void* stream);
+typedef struct {
+  const float* e_pos;        /* value rows of the N sorted positions  [L][N][32]      */
+  const int32_t* range_pos;  /* per level [n_l][2] (concatenated in level order)      */
+  int64_t n_pos;
+  float w_pos;
+  const float* e_nrm;        /* gradient rows of the K sorted normal locations [L][K][3][32] */
+  const int32_t* range_nrm;
+  const float* t_nrm;        /* [K][3] targets (sorted order)                          */
+  int64_t n_nrm;
+  float w_nrm;
+  float w_reg;
+} nksr_constraints_t;
+/* numeric assembly: fills col/val (CSR, int64 rowptr), rhs b, diag. cursor[n] must be zero. */
+NKSR_API int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c,
+                   const int32_t* cnt, const int64_t* rowptr, int32_t* col, float* val,
+                   float* rhs, float* diag, int32_t* cursor, void* stream);
+/* sort the finer-level (transposed) segment of every row by column: deterministic storage */
+NKSR_API int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, const int64_t* rowptr,
+                        int64_t row0, int64_t row1, int cap, int32_t* col, float* val,
+                        void* stream);
+
+/* ---- a4: PCG (solver_tol, examples/recons_waymo.py:33; verbose, models/nksr_net.py:97) ---- */
+NKSR_API int nksr_spmv(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
+              float* y, int64_t n, void* stream);
+NKSR_API size_t nksr_pcg_workspace_bytes(int64_t n);
+/* Jacobi-PCG from x=0. info[0]=iterations, info[1]=relative residual (host doubles). */
+NKSR_API int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val,
+                   const float* diag, const float* b, float* x, int64_t n, float tol,
+                   int max_iter, int check_every, void* ws, size_t ws_bytes, double* info,
+                   void* stream);
+
+/* ---- a5: field.evaluate_f (models/loss.py:189-198,225) ---- */
+NKSR_API int nksr_evaluate(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* alpha,
+                  const float* xyz, int64_t m, int want_grad, int approx_kernel_grad,
+                  float* f, float* grad, void* stream);
+
+/* ---- a7: field.extract_dual_mesh (models/nksr_net.py:214,284; examples/recons_simple.py:27) ---- */
+/* flag[i]=1 if the dual cell with min corner voxel i exists (all 8 voxels active) */
+NKSR_API int nksr_mesh_cell_flags(const nksr_svh_t* svh, int32_t* flag, void* stream);
+/* min-corner lattice coords (int32 xyz, units W/R) of flagged voxels, in voxel order */
+NKSR_API int nksr_mesh_stage0_cells(const nksr_svh_t* svh, const int32_t* flag, const int64_t* scan,
+                           int32_t refine, int32_t* cells, void* stream);
+/* split every cell into g^3 children of size size/g */
+NKSR_API int nksr_mesh_split_cells(const int32_t* cells, int64_t n, int32_t size, int32_t g,
+                          int32_t* out, void* stream);
+/* 8 corner keys per cell: morton(corner - origin) */
+NKSR_API int nksr_mesh_corner_keys(const int32_t* cells, int64_t n, int32_t size, int32_t ox, int32_t oy,
+                          int32_t oz, int64_t* keys8, void* stream);
+/* world positions of lattice keys: W*(0.5 + s/R) */
+NKSR_API int nksr_mesh_lattice_pos(const int64_t* keys, int64_t n, int32_t ox, int32_t oy, int32_t oz,
+                          float voxel_size, int32_t refine, float* xyz, void* stream);
+/* per cell: corner values via binary search of corner keys, case index, crossing flag */
+NKSR_API int nksr_mesh_classify(const int64_t* keys8, int64_t n_cells, const int64_t* ukeys,
+                       const float* uval, int64_t n_u, float* cval8, int32_t* mc_case,
+                       int32_t* crossing, void* stream);
+/* gather rows selected by an exclusive scan of flags */
+NKSR_API int nksr_compact_rows(const void* in, const int32_t* flag, const int64_t* scan, int64_t n,
+                      int32_t row_bytes, void* out, void* stream);
+NKSR_API size_t nksr_scan32_workspace_bytes(int64_t n);
+NKSR_API int nksr_exclusive_scan32(const int32_t* in, int64_t* out, int64_t n, void* ws, size_t ws_bytes,
+                          void* stream); /* out has n+1 entries */
+/* per crossing cell: triangle count and 12 edge keys (or -1) */
+NKSR_API int nksr_mesh_cell_edges(const int32_t* cells, const int32_t* mc_case, int64_t n, int32_t size,
+                         int32_t ox, int32_t oy, int32_t oz, int32_t* ntri, int64_t* ekeys12,
+                         void* stream);
+/* flag[i] = 1 at the first element of every run of equal non-negative keys (sorted input) */
+NKSR_API int nksr_run_heads(const int64_t* keys, int64_t n, int32_t* flag, void* stream);
+/* vertices of unique edge keys (src = first cell*12+edge owning it) */
+NKSR_API int nksr_mesh_vertices(const int64_t* uekeys, const int32_t* src, int64_t n_v,
+                       const int32_t* cells, const float* cval8, int32_t size,
+                       float voxel_size, int32_t refine, float* v, void* stream);
+NKSR_API int nksr_mesh_triangles(const int32_t* mc_case, const int64_t* ekeys12, const int64_t* tri_scan,
+                        int64_t n_cells, const int64_t* uekeys, int64_t n_v, int64_t* tri,
+                        void* stream);
+/* LayerField mask (models/nksr_net.py:132): 1 if x lies in an active voxel of level < adaptive_depth */
+NKSR_API int nksr_layer_mask(const nksr_svh_t* svh, const float* xyz, int64_t m, int adaptive_depth,
+                    float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NKSR_B200_H */

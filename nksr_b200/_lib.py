@@ -1,0 +1,204 @@
+"""ctypes binding of libnksr_b200.so (the C-ABI declared in include/nksr_b200.h).
+
+This is the reference-side stub a maintainer would add: plain pointers and
+sizes cross the boundary, torch only owns the memory and the stream.  There is NO fallback:
+if the shared library is missing, or a call returns a non-zero code, we raise -- callers in the
+reference treat RuntimeError as "skip / retry" (models/base_model.py:140-148).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+MAX_DEPTH = 8
+ROW_STRIDE = 32
+_LIB_NAME = "libnksr_b200.so"
+_here = os.path.dirname(os.path.abspath(__file__))
+
+
+class SvhT(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("voxel_size", C.c_float),
+                ("n", C.c_int64 * MAX_DEPTH), ("offset", C.c_int64 * MAX_DEPTH),
+                ("keys", C.c_void_p * MAX_DEPTH), ("parent", C.c_void_p * MAX_DEPTH),
+                ("child8", C.c_void_p * MAX_DEPTH), ("nbr27", C.c_void_p * MAX_DEPTH)]
+
+
+class FeatT(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("z", C.c_void_p * MAX_DEPTH)]
+
+
+class ConstraintsT(C.Structure):
+    _fields_ = [("e_pos", C.c_void_p), ("range_pos", C.c_void_p), ("n_pos", C.c_int64), ("w_pos", C.c_float),
+                ("e_nrm", C.c_void_p), ("range_nrm", C.c_void_p), ("t_nrm", C.c_void_p), ("n_nrm", C.c_int64),
+                ("w_nrm", C.c_float), ("w_reg", C.c_float)]
+
+
+_T = {"p": C.c_void_p, "q": C.c_int64, "i": C.c_int32, "f": C.c_float, "z": C.c_size_t,
+      "S": C.POINTER(SvhT), "F": C.POINTER(FeatT), "K": C.POINTER(ConstraintsT), "d": C.POINTER(C.c_double)}
+
+# name -> (return kind, argument kinds); mirrors include/nksr_b200.h one to one
+_SIGNATURES = {
+    "nksr_version": ("s", ""),
+    "nksr_error_string": ("s", "i"),
+    "nksr_point_half_keys": ("i", "pqfppp"),
+    "nksr_sort_workspace_bytes": ("z", "qi"),
+    "nksr_sort_keys": ("i", "ppqpzp"),
+    "nksr_sort_pairs": ("i", "ppppqpzp"),
+    "nksr_unique_workspace_bytes": ("z", "q"),
+    "nksr_unique_sorted": ("i", "pqipppzp"),
+    "nksr_splat_candidates": ("i", "pqpp"),
+    "nksr_parent_index": ("i", "pqpqppp"),
+    "nksr_child_table": ("i", "ppqpqp"),
+    "nksr_nbr27_search": ("i", "pqpp"),
+    "nksr_nbr27_from_parent": ("i", "ppqpppp"),
+    "nksr_decode_ijk": ("i", "pqipp"),
+    "nksr_locate": ("i", "Spqpp"),
+    "nksr_row_ranges": ("i", "pqpqp"),
+    "nksr_build_rows": ("i", "SFppqiipp"),
+    "nksr_gram_count": ("i", "Sppp"),
+    "nksr_scan_workspace_bytes": ("z", "q"),
+    "nksr_gram_rowptr": ("i", "ppqppzp"),
+    "nksr_gram_fill": ("i", "SFKppppppp" + "p"),
+    "nksr_gram_sort_down": ("i", "pppqqippp"),
+    "nksr_spmv": ("i", "pppppqp"),
+    "nksr_pcg_workspace_bytes": ("z", "q"),
+    "nksr_pcg_solve": ("i", "pppppp" + "qfii" + "pzdp"),
+    "nksr_evaluate": ("i", "SFppqiippp"),
+    "nksr_mesh_cell_flags": ("i", "Spp"),
+    "nksr_mesh_stage0_cells": ("i", "Sppipp"),
+    "nksr_mesh_split_cells": ("i", "pqiipp"),
+    "nksr_mesh_corner_keys": ("i", "pqiiiipp"),
+    "nksr_mesh_lattice_pos": ("i", "pqiiifipp"),
+    "nksr_mesh_classify": ("i", "pqppqpppp"),
+    "nksr_compact_rows": ("i", "pppqipp"),
+    "nksr_scan32_workspace_bytes": ("z", "q"),
+    "nksr_exclusive_scan32": ("i", "ppqpzp"),
+    "nksr_mesh_cell_edges": ("i", "ppqiiiippp"),
+    "nksr_run_heads": ("i", "pqpp"),
+    "nksr_mesh_vertices": ("i", "ppqppifipp"),
+    "nksr_mesh_triangles": ("i", "pppqpqpp"),
+    "nksr_layer_mask": ("i", "Spqipp"),
+}
+
+_lib = None
+
+
+class NksrError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_here, _LIB_NAME)
+
+
+def load():
+    """Load the CUDA library once.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise NksrError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "or `make -C nksr_b200/csrc` -- nksr_b200 has no CPU or PyTorch fallback")
+    lib = C.CDLL(path)
+    for name, (ret, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = {"i": C.c_int, "z": C.c_size_t, "s": C.c_char_p}[ret]
+        fn.argtypes = [_T[a] for a in args]
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def _conv(kind, v):
+    if kind == "p":
+        if v is None:
+            return None
+        if isinstance(v, torch.Tensor):
+            return v.data_ptr()
+        return int(v)
+    if kind in "SFK":
+        return C.byref(v)
+    return v
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream if torch.device(device).type == "cuda" else 0
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point; non-zero codes become NksrError."""
+    lib = load()
+    kinds = _SIGNATURES[name][1]
+    if len(kinds) != len(args):
+        raise TypeError(f"{name}: expected {len(kinds)} arguments, got {len(args)}")
+    fn = getattr(lib, name)
+    rc = fn(*[_conv(k, a) for k, a in zip(kinds, args)])
+    if _SIGNATURES[name][0] == "i" and rc != 0:
+        raise NksrError(f"{name} failed: {lib.nksr_error_string(rc).decode()} ({rc})")
+    return rc
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise NksrError(f"{what} must live on a CUDA device: nksr_b200 is a B200-only implementation "
+                        "(no CPU path; the CPU oracle under oracle/ is test infrastructure)")
+
+
+# ----------------------------------------------------------------------------- small helpers
+def _ws(nbytes: int, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def sort_keys(keys: torch.Tensor) -> torch.Tensor:
+    n = keys.numel()
+    out = torch.empty_like(keys)
+    if n:
+        nb = call("nksr_sort_workspace_bytes", n, 0)
+        ws = _ws(nb, keys.device)
+        call("nksr_sort_keys", keys, out, n, ws, nb, stream_ptr(keys.device))
+    return out
+
+
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor):
+    n = keys.numel()
+    ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+    if n:
+        nb = call("nksr_sort_workspace_bytes", n, 1)
+        ws = _ws(nb, keys.device)
+        call("nksr_sort_pairs", keys, ko, vals, vo, n, ws, nb, stream_ptr(keys.device))
+    return ko, vo
+
+
+def unique_sorted(keys: torch.Tensor, shift: int = 0) -> torch.Tensor:
+    n = keys.numel()
+    out = torch.empty_like(keys)
+    cnt = torch.zeros(1, dtype=torch.int64, device=keys.device)
+    if n:
+        nb = call("nksr_unique_workspace_bytes", n)
+        ws = _ws(nb, keys.device)
+        call("nksr_unique_sorted", keys, n, shift, out, cnt, ws, nb, stream_ptr(keys.device))
+    return out[: int(cnt.item())]
+
+
+def exclusive_scan32(flags: torch.Tensor) -> torch.Tensor:
+    n = flags.numel()
+    out = torch.empty(n + 1, dtype=torch.int64, device=flags.device)
+    nb = call("nksr_scan32_workspace_bytes", max(n, 1))
+    ws = _ws(nb, flags.device)
+    call("nksr_exclusive_scan32", flags, out, n, ws, nb, stream_ptr(flags.device))
+    return out
+
+
+def compact_rows(rows: torch.Tensor, flags: torch.Tensor, scan: torch.Tensor, count: int) -> torch.Tensor:
+    n = flags.numel()
+    row_bytes = rows.element_size() * (rows.numel() // max(n, 1)) if n else rows.element_size()
+    out = torch.empty((count,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    if n and count:
+        call("nksr_compact_rows", rows, flags, scan, n, row_bytes, out, stream_ptr(rows.device))
+    return out

@@ -1,0 +1,340 @@
+// Gram-matrix assembly A = E^T diag(w) E + reg*R into CSR.
+// Replaces the matrix build inside KernelField.solve_non_fused / fused_mode
+// (models/nksr_net.py:100-112, examples/recons_waymo.py:33).
+//
+// Layout (DESIGN.md SPEC S6): unknowns are ordered level-major, Morton inside a level.  Row
+// (l,i) stores, in this order, [same-level 125-stencil | coarser level l+1 (<=64) | ... | level
+// L-1 | finer-level entries (transposes)].  Only ACTIVE column voxels are stored.
+//
+// Numeric phase: one warp per row.  For each of the 27 voxels u around i, the constraint rows
+// whose containing voxel is u form one contiguous range (locations are Morton sorted); every
+// such row r contributes  w * E[r,i] * E[r, :]  and all rows of u share the same 27-stencils on
+// level l and on every coarser level, so lane s accumulates stencil slot s in a register and
+// the warp flushes once per u into a per-warp shared-memory tile indexed by structural slot --
+// no atomics, deterministic summation order.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kMaxSlots = 125 + 64 * (NKSR_MAX_DEPTH - 1);
+
+// same-level voxel at offset-space coords (nx,ny,nz) in the 125-neighbourhood of voxel i
+// (coords ux,uy,uz): through the parent's 27-stencil and its child table; top level: search.
+__device__ __forceinline__ int lookup_near(const nksr_svh_t& svh, int l, int i, int ux, int uy, int uz, int nx,
+                                           int ny, int nz) {
+  if (l + 1 < svh.depth) {
+    int p = __ldg(svh.parent[l] + i);
+    if (p < 0) return -1;
+    int ex = (nx >> 1) - (ux >> 1), ey = (ny >> 1) - (uy >> 1), ez = (nz >> 1) - (uz >> 1);
+    int pn = __ldg(svh.nbr27[l + 1] + (int64_t)p * 27 + (ex + 1) * 9 + (ey + 1) * 3 + (ez + 1));
+    if (pn < 0) return -1;
+    return __ldg(svh.child8[l + 1] + (int64_t)pn * 8 + (((nx & 1) << 2) | ((ny & 1) << 1) | (nz & 1)));
+  }
+  if (nx < 0 || ny < 0 || nz < 0) return -1;
+  return find_key(svh.keys[l], svh.n[l], morton3(nx, ny, nz));
+}
+
+struct RowGeom {
+  int ux, uy, uz;                 // offset-space coords of the row voxel
+  int anc[NKSR_MAX_DEPTH];        // ancestor index at level l+k (anc[0] = i)
+};
+
+__device__ __forceinline__ void row_geom(const nksr_svh_t& svh, int l, int i, RowGeom& g) {
+  morton3_decode(__ldg(svh.keys[l] + i), g.ux, g.uy, g.uz);
+  g.anc[0] = i;
+  int a = i;
+  for (int k = 1; l + k < svh.depth; ++k) {
+    a = a >= 0 ? __ldg(svh.parent[l + k - 1] + a) : -1;
+    g.anc[k] = a;
+  }
+}
+
+// column voxel (index at its level) of structural slot t of row (l,i); -1 when inactive.
+// t < 125: same level; else k = 1 + (t-125)/64 levels up, 4x4x4 candidate box from lo.
+__device__ __forceinline__ int slot_column(const nksr_svh_t& svh, int l, const RowGeom& g, int t, int& k_out) {
+  if (t < 125) {
+    k_out = 0;
+    int dx = t / 25 - 2, dy = (t / 5) % 5 - 2, dz = t % 5 - 2;
+    return lookup_near(svh, l, g.anc[0], g.ux, g.uy, g.uz, g.ux + dx, g.uy + dy, g.uz + dz);
+  }
+  int q = t - 125;
+  int k = 1 + (q >> 6);
+  k_out = k;
+  q &= 63;
+  int ox = q >> 4, oy = (q >> 2) & 3, oz = q & 3;
+  int cx = (((g.ux - 1) >> k) - 1) + ox, cy = (((g.uy - 1) >> k) - 1) + oy, cz = (((g.uz - 1) >> k) - 1) + oz;
+  if (cx > ((g.ux + 1) >> k) + 1 || cy > ((g.uy + 1) >> k) + 1 || cz > ((g.uz + 1) >> k) + 1) return -1;
+  int a = g.anc[k];
+  if (a < 0) return -1;
+  return lookup_near(svh, l + k, a, g.ux >> k, g.uy >> k, g.uz >> k, cx, cy, cz);
+}
+
+__device__ __forceinline__ void row_of_warp(const nksr_svh_t& svh, int64_t row, int& l, int& i) {
+  l = 0;
+  while (l + 1 < svh.depth && row >= svh.offset[l + 1]) ++l;
+  i = (int)(row - svh.offset[l]);
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_gram_count(nksr_svh_t svh, int64_t n_total, int32_t* __restrict__ cnt, int32_t* __restrict__ cnt_down) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  if (row >= n_total) return;
+  int l, i;
+  row_of_warp(svh, row, l, i);
+  RowGeom g;
+  row_geom(svh, l, i, g);
+  const int nslots = 125 + 64 * (svh.depth - 1 - l);
+  int c = 0;
+  for (int t0 = 0; t0 < nslots; t0 += 32) {
+    int t = t0 + lane, k = 0;
+    int col = t < nslots ? slot_column(svh, l, g, t, k) : -1;
+    if (col >= 0 && k > 0) atomicAdd(cnt_down + svh.offset[l + k] + col, 1);
+    c += __popc(__ballot_sync(0xffffffffu, col >= 0));
+  }
+  if (lane == 0) cnt[row] = c;
+}
+
+struct AddPair {
+  const int32_t* a;
+  const int32_t* b;
+  __host__ __device__ __forceinline__ int64_t operator()(const int64_t& i) const { return (int64_t)a[i] + b[i]; }
+};
+
+__global__ void k_set_last(const int32_t* cnt, const int32_t* cnt_down, int64_t n, int64_t* rowptr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) rowptr[n] = rowptr[n - 1] + cnt[n - 1] + cnt_down[n - 1];
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_total,
+            const int32_t* __restrict__ cnt, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col_out,
+            float* __restrict__ val_out, float* __restrict__ rhs, float* __restrict__ diag,
+            int32_t* __restrict__ cursor) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int64_t row = blockIdx.x * (int64_t)kWarps + wid;
+  if (row >= n_total) return;
+  int l, i;
+  row_of_warp(svh, row, l, i);
+  const int L = svh.depth;
+  const int nup = L - 1 - l;
+  const int nslots = 125 + 64 * nup;
+  float* acc = smem + wid * kMaxSlots;
+  for (int t = lane; t < nslots; t += 32) acc[t] = 0.f;
+  __syncwarp();
+  RowGeom g;
+  row_geom(svh, l, i, g);
+  const int64_t N = cs.n_pos, K = cs.n_nrm;
+  // per-level base offsets of the range tables (levels concatenated)
+  int64_t roff = 0;
+  for (int q = 0; q < l; ++q) roff += svh.n[q];
+  const int32_t* rp = cs.range_pos ? cs.range_pos + 2 * roff : nullptr;
+  const int32_t* rn = cs.range_nrm ? cs.range_nrm + 2 * roff : nullptr;
+  float bsum = 0.f;
+  int ldx, ldy, ldz;
+  slot_to_d(lane < 27 ? lane : 13, ldx, ldy, ldz);
+
+  for (int us = 0; us < 27; ++us) {
+    const int u = __ldg(svh.nbr27[l] + (int64_t)i * 27 + us);
+    if (u < 0) continue;
+    const int si = 26 - us;  // slot of i inside u's stencil
+    float r[NKSR_MAX_DEPTH];
+#pragma unroll
+    for (int k = 0; k < NKSR_MAX_DEPTH; ++k) r[k] = 0.f;
+    if (rp) {
+      const int rb = __ldg(rp + 2 * (int64_t)u), re = __ldg(rp + 2 * (int64_t)u + 1);
+      for (int q = rb; q < re; ++q) {
+        const float a = cs.w_pos * __ldg(cs.e_pos + ((int64_t)l * N + q) * NKSR_ROW_STRIDE + si);
+#pragma unroll
+        for (int k = 0; k < NKSR_MAX_DEPTH; ++k)
+          if (k <= nup) r[k] = fmaf(a, __ldg(cs.e_pos + ((int64_t)(l + k) * N + q) * NKSR_ROW_STRIDE + lane), r[k]);
+      }
+    }
+    if (rn) {
+      const int rb = __ldg(rn + 2 * (int64_t)u), re = __ldg(rn + 2 * (int64_t)u + 1);
+      for (int q = rb; q < re; ++q) {
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          const float a = cs.w_nrm * __ldg(cs.e_nrm + (((int64_t)l * K + q) * 3 + ax) * NKSR_ROW_STRIDE + si);
+          bsum = fmaf(a, __ldg(cs.t_nrm + (int64_t)q * 3 + ax), bsum);
+#pragma unroll
+          for (int k = 0; k < NKSR_MAX_DEPTH; ++k)
+            if (k <= nup)
+              r[k] = fmaf(a, __ldg(cs.e_nrm + (((int64_t)(l + k) * K + q) * 3 + ax) * NKSR_ROW_STRIDE + lane), r[k]);
+        }
+      }
+    }
+    // flush: every lane < 27 owns a distinct structural slot per level
+    if (lane < 27) {
+      int udx, udy, udz;
+      slot_to_d(us, udx, udy, udz);
+      acc[(udx + ldx + 2) * 25 + (udy + ldy + 2) * 5 + (udz + ldz + 2)] += r[0];
+      const int vx = g.ux + udx, vy = g.uy + udy, vz = g.uz + udz;  // coords of u
+#pragma unroll
+      for (int k = 1; k < NKSR_MAX_DEPTH; ++k) {
+        if (k <= nup) {
+          int ox = ((vx >> k) + ldx) - (((g.ux - 1) >> k) - 1);
+          int oy = ((vy >> k) + ldy) - (((g.uy - 1) >> k) - 1);
+          int oz = ((vz >> k) + ldz) - (((g.uz - 1) >> k) - 1);
+          acc[125 + 64 * (k - 1) + (ox << 4) + (oy << 2) + oz] += r[k];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // regulariser: R_{i,i+d} = w_reg * B3(d) * <z_i, z_{i+d}>  (SPEC S5)
+  if (cs.w_reg != 0.f && lane < 27) {
+    const int nb = __ldg(svh.nbr27[l] + (int64_t)i * 27 + lane);
+    if (nb >= 0) {
+      const int C = feat.channels;
+      const float* zi = feat.z[l] + (int64_t)i * C;
+      const float* zn = feat.z[l] + (int64_t)nb * C;
+      float d = 0.f;
+      for (int c = 0; c < C; ++c) d = fmaf(__ldg(zi + c), __ldg(zn + c), d);
+      const float bw = (ldx == 0 ? 0.75f : 0.125f) * (ldy == 0 ? 0.75f : 0.125f) * (ldz == 0 ? 0.75f : 0.125f);
+      acc[(ldx + 2) * 25 + (ldy + 2) * 5 + (ldz + 2)] += cs.w_reg * bw * d;
+    }
+  }
+  __syncwarp();
+  // write-out in structural order
+  const int64_t p0 = rowptr[row];
+  int written = 0;
+  for (int t0 = 0; t0 < nslots; t0 += 32) {
+    const int t = t0 + lane;
+    int k = 0;
+    const int c = t < nslots ? slot_column(svh, l, g, t, k) : -1;
+    const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
+    if (c >= 0) {
+      const int64_t p = p0 + written + __popc(m & ((1u << lane) - 1u));
+      const float v = acc[t];
+      const int64_t gc = svh.offset[l + k] + c;
+      col_out[p] = (int32_t)gc;
+      val_out[p] = v;
+      if (k == 0 && c == i) diag[row] = v;
+      if (k > 0) {  // transposed copy into the coarse row's finer-level segment
+        const int64_t q = rowptr[gc] + cnt[gc] + atomicAdd(cursor + gc, 1);
+        col_out[q] = (int32_t)row;
+        val_out[q] = v;
+      }
+    }
+    written += __popc(m);
+  }
+  if (lane == 0) rhs[row] = bsum;
+}
+
+// bitonic sort of each row's finer-level segment by column (block per row)
+__global__ void k_sort_down(const int32_t* __restrict__ cnt, const int32_t* __restrict__ cnt_down,
+                            const int64_t* __restrict__ rowptr, int64_t row0, int64_t n, int32_t* __restrict__ col,
+                            float* __restrict__ val, int cap) {
+  extern __shared__ unsigned char raw[];
+  int32_t* sc = reinterpret_cast<int32_t*>(raw);
+  float* sv = reinterpret_cast<float*>(raw) + cap;
+  const int64_t row = row0 + blockIdx.x;
+  if (row >= n) return;
+  const int m = cnt_down[row];
+  if (m <= 1 || m > cap) return;
+  const int64_t p0 = rowptr[row] + cnt[row];
+  int m2 = 1;
+  while (m2 < m) m2 <<= 1;
+  for (int t = threadIdx.x; t < m2; t += blockDim.x) {
+    sc[t] = t < m ? col[p0 + t] : 0x7fffffff;
+    sv[t] = t < m ? val[p0 + t] : 0.f;
+  }
+  __syncthreads();
+  for (int k = 2; k <= m2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < m2; t += blockDim.x) {
+        int p = t ^ j;
+        if (p > t) {
+          bool up = (t & k) == 0;
+          int a = sc[t], b = sc[p];
+          if ((a > b) == up) {
+            sc[t] = b; sc[p] = a;
+            float x = sv[t]; sv[t] = sv[p]; sv[p] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int t = threadIdx.x; t < m; t += blockDim.x) {
+    col[p0 + t] = sc[t];
+    val[p0 + t] = sv[t];
+  }
+}
+
+static int64_t total_unknowns(const nksr_svh_t* svh) {
+  return svh->offset[svh->depth - 1] + svh->n[svh->depth - 1];
+}
+
+}  // namespace
+
+extern "C" {
+
+int nksr_gram_count(const nksr_svh_t* svh, int32_t* cnt, int32_t* cnt_down, void* stream) {
+  if (!svh || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
+  const int64_t n = total_unknowns(svh);
+  if (n == 0) return NKSR_OK;
+  if (cudaMemsetAsync(cnt_down, 0, (size_t)n * sizeof(int32_t), as_stream(stream)) != cudaSuccess) return NKSR_E_CUDA;
+  k_gram_count<<<grid_for(n, kWarps), kWarps * 32, 0, as_stream(stream)>>>(*svh, n, cnt, cnt_down);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+size_t nksr_scan_workspace_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::CountingInputIterator<int64_t> cnt_it(0);
+  cub::TransformInputIterator<int64_t, AddPair, cub::CountingInputIterator<int64_t>> it(cnt_it,
+                                                                                        AddPair{nullptr, nullptr});
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, (int64_t*)nullptr, n);
+  return bytes + 256;
+}
+
+int nksr_gram_rowptr(const int32_t* cnt, const int32_t* cnt_down, int64_t n, int64_t* rowptr, void* ws,
+                     size_t ws_bytes, void* stream) {
+  if (n <= 0) return NKSR_E_INVALID;
+  cub::CountingInputIterator<int64_t> cnt_it(0);
+  cub::TransformInputIterator<int64_t, AddPair, cub::CountingInputIterator<int64_t>> it(cnt_it,
+                                                                                        AddPair{cnt, cnt_down});
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, it, rowptr, n);
+  if (need > ws_bytes) return NKSR_E_WORKSPACE;
+  if (cub::DeviceScan::ExclusiveSum(ws, need, it, rowptr, n, as_stream(stream)) != cudaSuccess) return NKSR_E_CUDA;
+  k_set_last<<<1, 32, 0, as_stream(stream)>>>(cnt, cnt_down, n, rowptr);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c, const int32_t* cnt,
+                   const int64_t* rowptr, int32_t* col, float* val, float* rhs, float* diag, int32_t* cursor,
+                   void* stream) {
+  if (!svh || !feat || !c || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
+  const int64_t n = total_unknowns(svh);
+  if (n == 0) return NKSR_OK;
+  const size_t smem = (size_t)kWarps * kMaxSlots * sizeof(float);
+  k_gram_fill<<<grid_for(n, kWarps), kWarps * 32, smem, as_stream(stream)>>>(*svh, *feat, *c, n, cnt, rowptr, col,
+                                                                             val, rhs, diag, cursor);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, const int64_t* rowptr, int64_t row0,
+                        int64_t row1, int cap, int32_t* col, float* val, void* stream) {
+  // one block per row in [row0,row1); segments longer than `cap` (a power of two <= 16384) are
+  // left in insertion order.
+  if (row1 <= row0) return NKSR_OK;
+  if (cap < 2 || cap > 16384 || (cap & (cap - 1))) return NKSR_E_INVALID;
+  if (cap * 8 > 48 * 1024 &&
+      cudaFuncSetAttribute(k_sort_down, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8) != cudaSuccess)
+    return NKSR_E_CUDA;
+  k_sort_down<<<(unsigned)(row1 - row0), cap >= 1024 ? 256 : 64, cap * 8, as_stream(stream)>>>(
+      cnt, cnt_down, rowptr, row0, row1, col, val, cap);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+// Kernel-row construction for the Gram assembly (row a3) and field evaluation (row a5).
+// Call sites replaced: KernelField.solve_non_fused (models/nksr_net.py:100-112) and
+// field.evaluate_f (models/loss.py:189-198,225).
+#include "kernel_eval.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+// one warp per (location, level): writes a 128-byte value row or three gradient rows
+template <bool GRAD>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, const int32_t* __restrict__ base,
+             int64_t m, bool fullgrad, float* __restrict__ e) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t total = m * svh.depth;
+  if (warp >= total) return;
+  const int l = (int)(warp / m);
+  const int64_t i = warp - (int64_t)l * m;
+  const int b = __ldg(base + (int64_t)l * m + i);
+  float* out = e + (GRAD ? ((int64_t)l * m + i) * 3 * NKSR_ROW_STRIDE : ((int64_t)l * m + i) * NKSR_ROW_STRIDE);
+  if (b < 0) {
+    out[lane] = 0.f;
+    if (GRAD) { out[32 + lane] = 0.f; out[64 + lane] = 0.f; }
+    return;
+  }
+  const float wl = svh.voxel_size * (float)(1 << l);
+  LaneKernel r = eval_level_lane<GRAD>(svh.keys[l], svh.nbr27[l], feat.z[l], feat.channels, l, wl,
+                                       __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), b,
+                                       fullgrad, lane);
+  if (GRAD) {
+    out[lane] = r.dk[0];
+    out[32 + lane] = r.dk[1];
+    out[64 + lane] = r.dk[2];
+  } else {
+    out[lane] = r.k;
+  }
+}
+
+// one warp per query: f(x) = sum_l sum_s alpha * K ; containing voxels found by top search + descent
+template <bool GRAD>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_evaluate(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ alpha, const float* __restrict__ xyz,
+           int64_t m, bool fullgrad, float* __restrict__ f, float* __restrict__ g) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= m) return;
+  const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
+  const float half_w = svh.voxel_size * 0.5f;
+  int u[3];
+  bool bad = false;
+  {
+    float p[3] = {px, py, pz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float q = floorf(__fdiv_rn(p[a], half_w));
+      if (!(q > -(float)(NKSR_HALF_OFFSET - 16) && q < (float)(NKSR_HALF_OFFSET - 16))) { bad = true; q = 0.f; }
+      u[a] = (int)q + NKSR_HALF_OFFSET;
+    }
+  }
+  const int L = svh.depth;
+  int idx = -1;
+  if (!bad && svh.n[L - 1] > 0)
+    idx = find_key(svh.keys[L - 1], svh.n[L - 1], morton3(u[0] >> L, u[1] >> L, u[2] >> L));
+  float accf = 0.f, accg[3] = {0.f, 0.f, 0.f};
+  for (int l = L - 1; l >= 0; --l) {
+    if (idx < 0) break;  // parent closure: nothing active below
+    const float wl = svh.voxel_size * (float)(1 << l);
+    LaneKernel r = eval_level_lane<GRAD>(svh.keys[l], svh.nbr27[l], feat.z[l], feat.channels, l, wl, px, py, pz,
+                                         idx, fullgrad, lane);
+    float a = r.nb >= 0 ? __ldg(alpha + svh.offset[l] + r.nb) : 0.f;
+    accf = fmaf(a, r.k, accf);
+    if (GRAD) {
+      accg[0] = fmaf(a, r.dk[0], accg[0]);
+      accg[1] = fmaf(a, r.dk[1], accg[1]);
+      accg[2] = fmaf(a, r.dk[2], accg[2]);
+    }
+    if (l > 0) {
+      int slot = (((u[0] >> l) & 1) << 2) | (((u[1] >> l) & 1) << 1) | ((u[2] >> l) & 1);
+      idx = __ldg(svh.child8[l] + (int64_t)idx * 8 + slot);
+    }
+  }
+  accf = warp_sum(accf);
+  if (GRAD) {
+    accg[0] = warp_sum(accg[0]);
+    accg[1] = warp_sum(accg[1]);
+    accg[2] = warp_sum(accg[2]);
+  }
+  if (lane == 0) {
+    f[i] = accf;
+    if (GRAD) { g[3 * i] = accg[0]; g[3 * i + 1] = accg[1]; g[3 * i + 2] = accg[2]; }
+  }
+}
+
+// LayerField mask: 1 when the containing voxel of some level < adaptive_depth is active
+__global__ void k_layer_mask(nksr_svh_t svh, const float* __restrict__ xyz, int64_t m, int adaptive_depth,
+                             float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float half_w = svh.voxel_size * 0.5f;
+  int u[3];
+  bool bad = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float q = floorf(__fdiv_rn(__ldg(xyz + 3 * i + a), half_w));
+    if (!(q > -(float)(NKSR_HALF_OFFSET - 16) && q < (float)(NKSR_HALF_OFFSET - 16))) { bad = true; q = 0.f; }
+    u[a] = (int)q + NKSR_HALF_OFFSET;
+  }
+  float r = 0.f;
+  if (!bad) {
+    int top = adaptive_depth < svh.depth ? adaptive_depth : svh.depth;
+    for (int l = 0; l < top; ++l) {
+      if (svh.n[l] == 0) continue;
+      int sh = l + 1;
+      if (find_key(svh.keys[l], svh.n[l], morton3(u[0] >> sh, u[1] >> sh, u[2] >> sh)) >= 0) { r = 1.f; break; }
+    }
+  }
+  out[i] = r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* xyz, const int32_t* base,
+                    int64_t m, int mode, int approx_kernel_grad, float* e, void* stream) {
+  if (!svh || !feat || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH || feat->channels < 1) return NKSR_E_INVALID;
+  if (m == 0) return NKSR_OK;
+  int64_t warps = m * svh->depth;
+  int grid = grid_for(warps, kWarpsPerBlock);
+  if (mode == 0)
+    k_build_rows<false><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m, false, e);
+  else
+    k_build_rows<true><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m,
+                                                                             !approx_kernel_grad, e);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_evaluate(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* alpha, const float* xyz, int64_t m,
+                  int want_grad, int approx_kernel_grad, float* f, float* grad, void* stream) {
+  if (!svh || !feat || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH || feat->channels < 1) return NKSR_E_INVALID;
+  if (m == 0) return NKSR_OK;
+  int grid = grid_for(m, kWarpsPerBlock);
+  if (want_grad)
+    k_evaluate<true><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, alpha, xyz, m,
+                                                                          !approx_kernel_grad, f, grad);
+  else
+    k_evaluate<false><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, alpha, xyz, m, false, f,
+                                                                           grad);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_layer_mask(const nksr_svh_t* svh, const float* xyz, int64_t m, int adaptive_depth, float* out,
+                    void* stream) {
+  if (!svh || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
+  if (m == 0) return NKSR_OK;
+  k_layer_mask<<<grid_for(m, 256), 256, 0, as_stream(stream)>>>(*svh, xyz, m, adaptive_depth, out);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+}  // extern "C"

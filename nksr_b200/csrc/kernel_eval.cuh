@@ -1,0 +1,92 @@
+// Per-(location, level) neural-kernel evaluation, one warp per location, lane = stencil slot.
+// K_l(x, i) = B3((x - c_i)/W_l) * <phi_l(x), z_i>,  phi_l(x) = trilinear interpolation of z
+// (DESIGN.md SPEC S4).  Shared by row building (Gram assembly) and field evaluation.
+#pragma once
+#include "common.cuh"
+
+struct LaneKernel {
+  int nb;       // neighbour voxel index of this lane's slot (-1: none / lane >= 27)
+  float k;      // K_l(x, nb)
+  float dk[3];  // grad_x K_l(x, nb)
+};
+
+// weights of neighbour d in {-1,0,1} along one axis at local coordinate tau in [-.5,.5)
+__device__ __forceinline__ void axis_weights(float tau, int d, float& b, float& db, float& t, float& dt) {
+  if (d == 0) {
+    b = 0.75f - tau * tau;
+    db = -2.f * tau;
+    t = tau >= 0.f ? 1.f - tau : 1.f + tau;
+    dt = tau >= 0.f ? -1.f : 1.f;
+  } else if (d < 0) {
+    float h = 0.5f - tau;
+    b = 0.5f * h * h;
+    db = -h;
+    t = tau >= 0.f ? 0.f : -tau;
+    dt = tau >= 0.f ? 0.f : -1.f;
+  } else {
+    float h = 0.5f + tau;
+    b = 0.5f * h * h;
+    db = h;
+    t = tau >= 0.f ? tau : 0.f;
+    dt = tau >= 0.f ? 1.f : 0.f;
+  }
+}
+
+// All 32 lanes must call.  base >= 0.  GRAD: also the gradient; FULLGRAD: include the
+// grad(phi) term (approx_kernel_grad == false).
+template <bool GRAD>
+__device__ __forceinline__ LaneKernel eval_level_lane(const int64_t* __restrict__ keys,
+                                                      const int32_t* __restrict__ nbr27,
+                                                      const float* __restrict__ z, int C, int level,
+                                                      float wl, float px, float py, float pz, int base,
+                                                      bool fullgrad, int lane) {
+  LaneKernel r;
+  int ux, uy, uz;
+  morton3_decode(__ldg(keys + base), ux, uy, uz);
+  const int off = level_offset(level);
+  // local coordinate in voxel units; the subtraction is done in fp64 to avoid cancellation
+  const double inv = 1.0 / (double)wl;
+  float tx = (float)((double)px * inv - ((double)(ux - off) + 0.5));
+  float ty = (float)((double)py * inv - ((double)(uy - off) + 0.5));
+  float tz = (float)((double)pz * inv - ((double)(uz - off) + 0.5));
+  int dx, dy, dz;
+  slot_to_d(lane < 27 ? lane : 13, dx, dy, dz);
+  float bx, dbx, ttx, dtx, by, dby, tty, dty, bz, dbz, ttz, dtz;
+  axis_weights(tx, dx, bx, dbx, ttx, dtx);
+  axis_weights(ty, dy, by, dby, tty, dty);
+  axis_weights(tz, dz, bz, dbz, ttz, dtz);
+  r.nb = lane < 27 ? __ldg(nbr27 + (int64_t)base * 27 + lane) : -1;
+  const bool ok = r.nb >= 0;
+  const float B3 = bx * by * bz;
+  const float T3 = ok ? ttx * tty * ttz : 0.f;
+  float dT3[3];
+  if (GRAD) {
+    dT3[0] = ok ? dtx * tty * ttz : 0.f;
+    dT3[1] = ok ? ttx * dty * ttz : 0.f;
+    dT3[2] = ok ? ttx * tty * dtz : 0.f;
+  }
+  float dot = 0.f, ddot[3] = {0.f, 0.f, 0.f};
+  const float* zr = z + (int64_t)(ok ? r.nb : 0) * C;
+  for (int c = 0; c < C; ++c) {
+    float zc = ok ? __ldg(zr + c) : 0.f;
+    float phi = warp_sum(T3 * zc);
+    dot = fmaf(phi, zc, dot);
+    if (GRAD && fullgrad) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float dphi = warp_sum(dT3[a] * zc);
+        ddot[a] = fmaf(dphi, zc, ddot[a]);
+      }
+    }
+  }
+  r.k = ok ? B3 * dot : 0.f;
+  if (GRAD) {
+    const float iw = 1.f / wl;
+    r.dk[0] = ok ? (dbx * by * bz * dot + B3 * ddot[0]) * iw : 0.f;
+    r.dk[1] = ok ? (bx * dby * bz * dot + B3 * ddot[1]) * iw : 0.f;
+    r.dk[2] = ok ? (bx * by * dbz * dot + B3 * ddot[2]) * iw : 0.f;
+  } else {
+    r.dk[0] = r.dk[1] = r.dk[2] = 0.f;
+  }
+  return r;
+}

@@ -1,0 +1,342 @@
+"""Implicit fields -- host mirror of nksr.fields.{KernelField, NeuralField, LayerField, PCNNField}.
+
+Reference contract (closed wheel; call sites only):
+  KernelField(svh, interpolator, features, approx_kernel_grad)      models/nksr_net.py:91-96
+  .solver_config['verbose']                                          models/nksr_net.py:97-98
+  .solve_non_fused(pos_xyz, normal_xyz, normal_value, pos_weight,
+                   normal_weight, reg_weight)                        models/nksr_net.py:105-112
+  .evaluate_f(xyz, grad) -> .value / .gradient ; .evaluate_f_bar     models/loss.py:99,189-198,225
+  .set_mask_field / .set_texture_field / .to_ / .extract_dual_mesh   models/nksr_net.py:133,214,284
+  NeuralField(svh, decoder, features).set_level_set(v)               models/nksr_net.py:115-130
+  LayerField(svh, adaptive_depth)                                    models/nksr_net.py:132
+  PCNNField(xyz, color)                                              examples/recons_colored_mesh.py:28
+The arithmetic is in libnksr_b200.so; the algorithm is fixed in DESIGN.md (SPEC S3-S7).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import call, stream_ptr
+from .svh import SparseFeatureHierarchy
+
+
+class EvaluationResult(SimpleNamespace):
+    """`.value` (M,) and `.gradient` (M,3) as consumed at models/loss.py:189-198."""
+
+
+class BaseField:
+    def __init__(self, svh: SparseFeatureHierarchy):
+        self.svh = svh
+        self.mask_field: Optional["BaseField"] = None
+        self.texture_field = None
+        self.level_set = 0.0
+
+    def set_mask_field(self, mask_field):
+        self.mask_field = mask_field
+
+    def set_texture_field(self, texture_field):
+        self.texture_field = texture_field
+
+    def set_level_set(self, v: float):
+        self.level_set = float(v)
+
+    def evaluate_f(self, xyz: torch.Tensor, grad: bool = False) -> EvaluationResult:
+        raise NotImplementedError
+
+    def mask(self, xyz: torch.Tensor) -> torch.Tensor:
+        """bool (M,): True where geometry is kept by this field used as a mask."""
+        raise NotImplementedError
+
+    def to_(self, device):
+        self.svh.to_(device)
+        if self.mask_field is not None:
+            self.mask_field.to_(device)
+        return self
+
+    def extract_dual_mesh(self, grid_upsample: int = 1, mise_iter: int = 0, max_points: int = -1):
+        from .meshing import extract_dual_mesh
+        return extract_dual_mesh(self, grid_upsample=grid_upsample, mise_iter=mise_iter, max_points=max_points)
+
+
+def _as_level_list(features, depth):
+    if isinstance(features, dict):
+        return [features.get(d, None) for d in range(depth)]
+    return [features[d] if d < len(features) else None for d in range(depth)]
+
+
+class KernelField(BaseField):
+    def __init__(self, svh: SparseFeatureHierarchy, interpolator=None, features=None,
+                 approx_kernel_grad: bool = False):
+        super().__init__(svh)
+        self.approx_kernel_grad = bool(approx_kernel_grad)
+        self.solver_config = {"verbose": False, "tol": 1.0e-5, "max_iter": 2000, "check_every": 10}
+        self.interpolator = interpolator
+        self.alpha: Optional[torch.Tensor] = None
+        self.solve_info = {}
+        self.system = None          # kept for inspection / tests when solver_config['keep_system']
+        self._set_features(features)
+
+    # -- features: z_l = interpolator_l(basis_features_l), one (n_l, C) fp32 block per level
+    def _set_features(self, features):
+        depth, dev = self.svh.depth, self.svh.device
+        feats = _as_level_list(features, depth)
+        z, C_ = [], None
+        for l in range(depth):
+            f = feats[l]
+            n = self.svh.num_voxels(l)
+            if f is None:
+                z.append(None)
+                continue
+            if f.shape[0] != n:
+                raise ValueError(f"features[{l}] has {f.shape[0]} rows but level {l} has {n} voxels")
+            f = f.detach().to(dev, torch.float32)
+            if self.interpolator is not None:
+                mod = self.interpolator[l] if not isinstance(self.interpolator, dict) else self.interpolator[str(l)]
+                with torch.no_grad():
+                    f = mod(f)
+            f = f.contiguous()
+            C_ = f.shape[1] if C_ is None else C_
+            if f.shape[1] != C_:
+                raise ValueError("all levels must share one kernel_dim")
+            z.append(f)
+        if C_ is None:
+            raise ValueError("KernelField needs basis features on at least one level")
+        if not (1 <= C_ <= 32):
+            raise ValueError("kernel_dim must be in 1..32")
+        self.z = [t if t is not None else torch.zeros((self.svh.num_voxels(l), C_), device=dev)
+                  for l, t in enumerate(z)]
+        self.channels = C_
+        self._feat_view = None
+
+    def feat_view(self) -> _lib.FeatT:
+        if self._feat_view is None:
+            v = _lib.FeatT()
+            v.channels = self.channels
+            for l in range(self.svh.depth):
+                v.z[l] = self.z[l].data_ptr()
+            self._feat_view = v
+        return self._feat_view
+
+    # ------------------------------------------------------------------ solve
+    def _sorted_rows(self, xyz: torch.Tensor, mode: int, extra: Optional[torch.Tensor] = None):
+        """Morton-sort locations, locate them on every level, build their kernel rows."""
+        svh, dev = self.svh, xyz.device
+        st = stream_ptr(dev)
+        m = xyz.shape[0]
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        hk = torch.empty(m, dtype=torch.int64, device=dev)
+        call("nksr_point_half_keys", xyz, m, svh.voxel_size, hk, status, st)
+        _, perm = _lib.sort_pairs(hk, torch.arange(m, dtype=torch.int32, device=dev))
+        perm = perm.long()
+        xs = xyz[perm].contiguous()
+        ex = extra[perm].contiguous() if extra is not None else None
+        base = svh.locate(xs)
+        n_total = svh.num_unknowns
+        ranges = torch.empty((n_total, 2), dtype=torch.int32, device=dev)
+        offs = svh.offsets
+        for l in range(svh.depth):
+            call("nksr_row_ranges", base[l], m, ranges[offs[l]:], svh.num_voxels(l), st)
+        width = _lib.ROW_STRIDE * (3 if mode else 1)
+        e = torch.empty((svh.depth, m, width), dtype=torch.float32, device=dev)
+        call("nksr_build_rows", svh.view(), self.feat_view(), xs, base, m, mode,
+             int(self.approx_kernel_grad), e, st)
+        return xs, ex, base, ranges, e
+
+    def solve(self, pos_xyz, normal_xyz=None, normal_value=None, pos_weight=1.0, normal_weight=1.0,
+              reg_weight=1.0, fused_mode: bool = False):
+        """Assemble A = E^T W E + reg R (CSR) and solve A alpha = E^T W t with Jacobi-PCG."""
+        svh = self.svh
+        dev = svh.device
+        _lib.require_cuda(pos_xyz, "pos_xyz")
+        st = stream_ptr(dev)
+        n = svh.num_unknowns
+        if n == 0:
+            raise _lib.NksrError("empty hierarchy: nothing to solve")
+        if n >= 2 ** 31:
+            raise _lib.NksrError("more than 2^31 unknowns: shard the cloud (chunk_size)")
+        pos_xyz = pos_xyz.detach().to(dev, torch.float32).contiguous()
+        cs = _lib.ConstraintsT()
+        keep = []
+        _, _, _, range_pos, e_pos = self._sorted_rows(pos_xyz, 0)
+        keep += [range_pos, e_pos]
+        cs.e_pos, cs.range_pos, cs.n_pos, cs.w_pos = e_pos.data_ptr(), range_pos.data_ptr(), pos_xyz.shape[0], float(pos_weight)
+        if normal_xyz is not None and normal_xyz.shape[0] > 0:
+            normal_xyz = normal_xyz.detach().to(dev, torch.float32).contiguous()
+            normal_value = normal_value.detach().to(dev, torch.float32).contiguous()
+            _, t_nrm, _, range_nrm, e_nrm = self._sorted_rows(normal_xyz, 1, normal_value)
+            keep += [t_nrm, range_nrm, e_nrm]
+            cs.e_nrm, cs.range_nrm, cs.t_nrm = e_nrm.data_ptr(), range_nrm.data_ptr(), t_nrm.data_ptr()
+            cs.n_nrm, cs.w_nrm = normal_xyz.shape[0], float(normal_weight)
+        else:
+            cs.e_nrm = cs.range_nrm = cs.t_nrm = None
+            cs.n_nrm, cs.w_nrm = 0, 0.0
+        cs.w_reg = float(reg_weight)
+
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        cnt_down = torch.empty(n, dtype=torch.int32, device=dev)
+        call("nksr_gram_count", svh.view(), cnt, cnt_down, st)
+        rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        nb = call("nksr_scan_workspace_bytes", n)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        call("nksr_gram_rowptr", cnt, cnt_down, n, rowptr, ws, nb, st)
+        nnz = int(rowptr[-1].item())
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz, dtype=torch.float32, device=dev)
+        rhs = torch.empty(n, dtype=torch.float32, device=dev)
+        diag = torch.zeros(n, dtype=torch.float32, device=dev)
+        cursor = torch.zeros(n, dtype=torch.int32, device=dev)
+        call("nksr_gram_fill", svh.view(), self.feat_view(), cs, cnt, rowptr, col, val, rhs, diag, cursor, st)
+        # deterministic storage order of the transposed (finer-level) segments
+        offs = svh.offsets
+        for l in range(1, svh.depth):
+            if svh.num_voxels(l) == 0:
+                continue
+            mx = int(cnt_down[offs[l]:offs[l + 1]].max().item())
+            if mx > 1:
+                cap = max(2, 1 << (mx - 1).bit_length())
+                call("nksr_gram_sort_down", cnt, cnt_down, rowptr, offs[l], offs[l + 1], min(cap, 16384), col, val, st)
+        del keep
+        alpha = torch.empty(n, dtype=torch.float32, device=dev)
+        nb = call("nksr_pcg_workspace_bytes", n)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        info = (C.c_double * 2)()
+        call("nksr_pcg_solve", rowptr, col, val, diag, rhs, alpha, n, float(self.solver_config["tol"]),
+             int(self.solver_config["max_iter"]), int(self.solver_config["check_every"]), ws, nb, info, st)
+        self.alpha = alpha
+        self.solve_info = {"iterations": int(info[0]), "relative_residual": float(info[1]), "n": n, "nnz": nnz}
+        if self.solver_config.get("verbose"):
+            print(f"[nksr_b200] PCG: n={n} nnz={nnz} iters={int(info[0])} relres={float(info[1]):.3e}")
+        if self.solver_config.get("keep_system"):
+            self.system = SimpleNamespace(rowptr=rowptr, col=col, val=val, rhs=rhs, diag=diag, cnt=cnt,
+                                          cnt_down=cnt_down)
+        return self
+
+    # the reference exposes both spellings; both run the same fused assembly here
+    def solve_non_fused(self, pos_xyz, normal_xyz, normal_value, pos_weight, normal_weight, reg_weight):
+        return self.solve(pos_xyz, normal_xyz, normal_value, pos_weight, normal_weight, reg_weight)
+
+    # ------------------------------------------------------------------ evaluation
+    def evaluate_f(self, xyz: torch.Tensor, grad: bool = False) -> EvaluationResult:
+        if self.alpha is None:
+            raise _lib.NksrError("KernelField.evaluate_f called before solve()")
+        _lib.require_cuda(xyz, "xyz")
+        xyz = xyz.detach().to(self.svh.device, torch.float32).contiguous()
+        m = xyz.shape[0]
+        f = torch.empty(m, dtype=torch.float32, device=xyz.device)
+        g = torch.empty((m, 3), dtype=torch.float32, device=xyz.device) if grad else None
+        call("nksr_evaluate", self.svh.view(), self.feat_view(), self.alpha, xyz, m, int(grad),
+             int(self.approx_kernel_grad), f, g, stream_ptr(xyz.device))
+        return EvaluationResult(value=f, gradient=g)
+
+    def evaluate_f_bar(self, xyz: torch.Tensor) -> torch.Tensor:
+        """Occupancy-style value (> 0 inside, models/loss.py:99); masked-out regions read as outside."""
+        f = self.evaluate_f(xyz).value
+        if self.mask_field is not None:
+            f = torch.where(self.mask_field.mask(xyz), f, -f.abs())
+        return f
+
+    def mask(self, xyz):
+        return self.evaluate_f(xyz).value >= self.level_set
+
+    def to_(self, device):
+        super().to_(device)
+        device = torch.device(device)
+        self.z = [t.to(device) for t in self.z]
+        if self.alpha is not None:
+            self.alpha = self.alpha.to(device)
+        self._feat_view = None
+        return self
+
+
+class LayerField(BaseField):
+    """Mask = inside an active voxel of one of the finest `adaptive_depth` levels."""
+
+    def __init__(self, svh: SparseFeatureHierarchy, adaptive_depth: int):
+        super().__init__(svh)
+        self.adaptive_depth = int(adaptive_depth)
+        self.level_set = 0.5
+
+    def evaluate_f(self, xyz, grad=False):
+        _lib.require_cuda(xyz, "xyz")
+        xyz = xyz.detach().to(torch.float32).contiguous()
+        out = torch.empty(xyz.shape[0], dtype=torch.float32, device=xyz.device)
+        call("nksr_layer_mask", self.svh.view(), xyz, xyz.shape[0], self.adaptive_depth, out, stream_ptr(xyz.device))
+        return EvaluationResult(value=out, gradient=None)
+
+    def mask(self, xyz):
+        return self.evaluate_f(xyz).value >= self.level_set
+
+
+class NeuralField(BaseField):
+    """MLP-decoded field over trilinearly interpolated voxel features (used as the UDF mask,
+    models/nksr_net.py:124-130).  The decoder is a PyTorch module and stays on PyTorch
+    (north_star: the network is not part of the hot path); interpolation uses the SVH tables."""
+
+    def __init__(self, svh: SparseFeatureHierarchy, decoder, features):
+        super().__init__(svh)
+        self.decoder = decoder
+        self.features = _as_level_list(features, svh.depth)
+
+    def _interp(self, xyz):
+        svh = self.svh
+        base = svh.locate(xyz).long()
+        out = None
+        for l in range(svh.depth):
+            f = self.features[l]
+            if f is None or svh.num_voxels(l) == 0:
+                continue
+            w = svh.voxel_size * (2 ** l)
+            b = base[l]
+            ok = b >= 0
+            bc = b.clamp(min=0)
+            ijk = SparseFeatureHierarchyCoords.ijk(svh, l)[bc].to(torch.float32)
+            tau = xyz / w - (ijk + 0.5)
+            nb = svh.nbr27[l][bc].long()
+            acc = torch.zeros((xyz.shape[0], f.shape[1]), device=xyz.device, dtype=torch.float32)
+            d = torch.tensor([-1.0, 0.0, 1.0], device=xyz.device)
+            tw = (1.0 - (tau[:, :, None] - d[None, None, :]).abs()).clamp(min=0.0)      # (M,3,3)
+            w27 = (tw[:, 0, :, None, None] * tw[:, 1, None, :, None] * tw[:, 2, None, None, :]).reshape(-1, 27)
+            for s in range(27):
+                idx = nb[:, s]
+                good = ok & (idx >= 0)
+                acc += torch.where(good[:, None], f[idx.clamp(min=0)] * w27[:, s:s + 1], torch.zeros_like(acc))
+            out = acc if out is None else torch.cat([out, acc], dim=1)
+        return out
+
+    def evaluate_f(self, xyz, grad=False):
+        xyz = xyz.detach().to(self.svh.device, torch.float32).contiguous()
+        with torch.no_grad():
+            v = self.decoder(self._interp(xyz)).reshape(-1)
+        return EvaluationResult(value=v, gradient=None)
+
+    def mask(self, xyz):
+        # UDF semantics: keep geometry closer than the level set to the data
+        return self.evaluate_f(xyz).value <= self.level_set
+
+
+class SparseFeatureHierarchyCoords:
+    @staticmethod
+    def ijk(svh, l):
+        from .svh import SparseIndexGrid
+        return SparseIndexGrid(svh, l).active_grid_coords()
+
+
+class PCNNField:
+    """Nearest-neighbour colour texture (examples/recons_colored_mesh.py:28).  'Next' row f3 of
+    SURVEY section 8: chunked brute-force torch implementation, not a hot-path kernel yet."""
+
+    def __init__(self, xyz: torch.Tensor, color: torch.Tensor):
+        self.xyz, self.color = xyz, color
+
+    def evaluate_f(self, q: torch.Tensor, grad=False):
+        out = torch.empty((q.shape[0], self.color.shape[1]), device=q.device, dtype=self.color.dtype)
+        step = max(1, (1 << 24) // max(self.xyz.shape[0], 1))
+        for s in range(0, q.shape[0], step):
+            d = torch.cdist(q[s:s + step], self.xyz)
+            out[s:s + step] = self.color[d.argmin(dim=1)]
+        return EvaluationResult(value=out, gradient=None)

@@ -1,0 +1,138 @@
+"""NKSRNetwork stand-in (PyTorch).
+
+The reference's sparse-conv encoder / U-Net lives in the closed wheel and its pretrained
+weights are a network download (models/nksr_net.py:35-38, README.md:108-110).  BASELINE.json's
+north_star keeps the network on PyTorch and outside the hot path, so this module is a small,
+seeded, deterministic replacement that produces the SAME OUTPUT CONTRACT the hot path consumes
+(models/nksr_net.py:73-78, 93-94, 101, 117-118, 127-128):
+
+    feat = network.encoder(xyz, point_feat, svh, 0)
+    feat, dec_svh, udf_svh = network.unet(feat, svh, adaptive_depth=..., gt_decoder_svh=...)
+    feat.basis_features[d]  (n_d, kernel_dim)   feat.normal_features[d]  (n_d, 3)
+    feat.structure_features[d] (n_d, 3)         feat.udf_features[d]
+    network.interpolators / .sdf_decoder / .udf_decoder
+
+Normals are the pooled input normals (or view directions) -- i.e. the "prediction" is
+geometric, not learned; kernel features are a seeded perturbation of a constant, which makes
+the kernel close to the pure Bezier kernel (well conditioned).  Documented as synthetic in
+bench.py (`"data": "synthetic"`).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from .svh import SparseFeatureHierarchy
+
+_DEFAULTS = dict(kernel_dim=4, tree_depth=4, adaptive_depth=2, feature="normal",
+                 interpolator=dict(n_hidden=2, hidden_dim=16), udf=dict(enabled=False), seed=0)
+
+
+def _get(hp, key, default):
+    if hp is None:
+        return default
+    if isinstance(hp, dict):
+        return hp.get(key, default)
+    return getattr(hp, key, default)
+
+
+class ResidualMLP(nn.Module):
+    def __init__(self, dim, hidden, n_hidden, scale=0.1):
+        super().__init__()
+        layers, d = [], dim
+        for _ in range(max(n_hidden, 0)):
+            layers += [nn.Linear(d, hidden), nn.ReLU()]
+            d = hidden
+        layers.append(nn.Linear(d, dim))
+        self.net = nn.Sequential(*layers)
+        self.scale = scale
+
+    def forward(self, x):
+        return x + self.scale * torch.tanh(self.net(x))
+
+
+class FeatureBundle(SimpleNamespace):
+    pass
+
+
+class NKSRNetwork(nn.Module):
+    def __init__(self, hparams=None, **overrides):
+        super().__init__()
+        hp = {k: _get(hparams, k, v) for k, v in _DEFAULTS.items()}
+        hp.update(overrides)
+        self.kernel_dim = int(hp["kernel_dim"])
+        self.tree_depth = int(hp["tree_depth"])
+        self.adaptive_depth = int(hp["adaptive_depth"])
+        self.feature = hp["feature"]
+        interp = hp["interpolator"]
+        gen = torch.Generator().manual_seed(int(hp["seed"]))
+        state = torch.random.get_rng_state()
+        torch.manual_seed(int(hp["seed"]))
+        try:
+            C = self.kernel_dim
+            self.basis_heads = nn.ModuleList([nn.Linear(4, C) for _ in range(self.tree_depth)])
+            self.interpolators = nn.ModuleList([
+                ResidualMLP(C, int(_get(interp, "hidden_dim", 16)), int(_get(interp, "n_hidden", 2)))
+                for _ in range(self.tree_depth)])
+            self.structure_heads = nn.ModuleList([nn.Linear(4, 3) for _ in range(self.tree_depth)])
+            self.sdf_decoder = nn.Sequential(nn.Linear(C, 16), nn.ReLU(), nn.Linear(16, 1))
+            self.udf_decoder = nn.Sequential(nn.Linear(C, 16), nn.ReLU(), nn.Linear(16, 1))
+        finally:
+            torch.random.set_rng_state(state)
+        del gen
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    # ---- encoder: pool point features into the voxels of every level ---------------------
+    @torch.no_grad()
+    def encoder(self, xyz: torch.Tensor, feat, svh: SparseFeatureHierarchy, depth: int = 0):
+        base = svh.locate(xyz).long()                                   # (L, N)
+        pooled = []
+        ones = torch.ones((xyz.shape[0], 1), device=xyz.device)
+        src = torch.cat([feat.to(torch.float32) if feat is not None else torch.zeros_like(xyz), ones], dim=1)
+        for l in range(svh.depth):
+            n = svh.num_voxels(l)
+            acc = torch.zeros((n, 4), device=xyz.device)
+            ok = base[l] >= 0
+            acc.index_add_(0, base[l][ok], src[ok])
+            # smooth over the 27-neighbourhood so that splat-only voxels receive a value
+            nb = svh.nbr27[l].long()
+            gathered = torch.where((nb >= 0)[:, :, None], acc[nb.clamp(min=0)], torch.zeros((), device=xyz.device))
+            pooled.append(gathered.sum(dim=1))
+        return SimpleNamespace(svh=svh, pooled=pooled)
+
+    # ---- "U-Net": heads on the pooled statistics; hierarchy passes through -----------------
+    @torch.no_grad()
+    def unet(self, feat, svh: SparseFeatureHierarchy, adaptive_depth: int = None, gt_decoder_svh=None):
+        dec_svh = gt_decoder_svh if gt_decoder_svh is not None else svh
+        C = self.kernel_dim
+        basis, normal, structure, udf = {}, {}, {}, {}
+        up = None
+        for l in range(svh.depth - 1, -1, -1):
+            s = feat.pooled[l]
+            cnt = s[:, 3:4]
+            mean = s[:, :3] / cnt.clamp(min=1.0)
+            nrm = mean / (mean.norm(dim=1, keepdim=True) + 1e-6)
+            if up is not None and svh.parent[l] is not None:           # fill empties from the parent
+                nrm = torch.where(cnt > 0, nrm, up[svh.parent[l].long()])
+            up = nrm
+            x = torch.cat([nrm, torch.log1p(cnt)], dim=1)
+            basis[l] = (1.0 + 0.1 * torch.tanh(self.basis_heads[l](x))) / (C ** 0.5)
+            normal[l] = nrm
+            structure[l] = self.structure_heads[l](x)
+            udf[l] = basis[l]
+        out = FeatureBundle(basis_features=basis, normal_features=normal, structure_features=structure,
+                            udf_features=udf)
+        return out, dec_svh, dec_svh
+
+
+def load_checkpoint_from_url(url: str):
+    """nksr.configs.load_checkpoint_from_url (models/nksr_net.py:17,37-38).  There is no network
+    in this environment: only local paths are honoured; URLs raise."""
+    import os
+    if os.path.exists(url):
+        return torch.load(url, map_location="cpu")
+    raise RuntimeError(f"cannot fetch checkpoint '{url}': no network access; the B200 build uses the seeded "
+                       "stand-in network (nksr_b200/network.py)")

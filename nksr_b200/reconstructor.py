@@ -1,0 +1,252 @@
+"""Reconstructor -- host mirror of nksr.Reconstructor.
+
+Reference contract (closed wheel; call sites only):
+  Reconstructor(device); .chunk_tmp_device; .network       examples/recons_simple.py:25,
+                                                            examples/recons_by_chunk.py:26-27
+  .reconstruct(xyz, normal=None, sensor=None, detail_level=0.0, voxel_size=None,
+               chunk_size=None, preprocess_fn=None, approx_kernel_grad=, solver_tol=,
+               fused_mode=)                                  examples/recons_waymo.py:30-37,
+                                                            NKSR-USAGE.md:126-137
+  get_estimate_normal_preprocess_fn(knn, max_angle_deg)     examples/recons_waymo.py:36
+The wiring of one reconstruction (SVH -> network -> KernelField -> solve -> mask) follows the
+open training model, models/nksr_net.py:57-133, including its constraint weights.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, stream_ptr
+from .fields import BaseField, EvaluationResult, KernelField, LayerField
+from .meshing import DualMesh
+from .network import NKSRNetwork
+from .svh import SparseFeatureHierarchy
+
+DEFAULT_VOXEL_SIZE = 0.1          # configs/default/train.yaml:11
+POS_WEIGHT = 1.0e4                # configs/default/train.yaml:27-29 (solver.pos_weight)
+NORMAL_WEIGHT = 1.0e4             # solver.normal_weight
+
+
+def _count_voxels(xyz: torch.Tensor, w: float) -> int:
+    n = xyz.shape[0]
+    hk = torch.empty(n, dtype=torch.int64, device=xyz.device)
+    status = torch.zeros(1, dtype=torch.int32, device=xyz.device)
+    call("nksr_point_half_keys", xyz, n, float(w), hk, status, stream_ptr(xyz.device))
+    return int(_lib.unique_sorted(_lib.sort_keys(hk), 3).numel())
+
+
+def voxel_size_from_detail(xyz: torch.Tensor, detail_level: float) -> float:
+    """detail_level in [0,1] -> finest voxel size such that the cloud has on average
+    8 * 4^-detail points per occupied voxel (our definition; the reference only documents the
+    knob's direction, NKSR-USAGE.md:129-131).  Log-bisection on the occupied-voxel count."""
+    d = min(max(float(detail_level), 0.0), 1.0)
+    target = 8.0 * (0.25 ** d)
+    ext = float((xyz.max(dim=0).values - xyz.min(dim=0).values).max().item())
+    lo, hi = max(ext * 1e-5, 1e-9), max(ext, 1e-6)
+    n = xyz.shape[0]
+    for _ in range(24):
+        mid = math.sqrt(lo * hi)
+        if n / max(_count_voxels(xyz, mid), 1) > target:
+            hi = mid
+        else:
+            lo = mid
+    return math.sqrt(lo * hi)
+
+
+def get_estimate_normal_preprocess_fn(knn: int = 64, max_angle_deg: float = 85.0) -> Callable:
+    """Normal estimation + sensor-side orientation + grazing-angle filter, following the open CPU
+    twin examples/recons_waymo_cpu.py:21-41.  Neighbourhoods are voxel neighbourhoods sized to
+    hold ~knn points (PCA over the 27 voxels around the point) instead of exact kNN -- SURVEY
+    section 8(f) row 1 ('next'); runs in PyTorch on the device."""
+
+    def fn(xyz: torch.Tensor, normal: Optional[torch.Tensor], sensor: Optional[torch.Tensor]):
+        assert normal is None, "normal already exists"
+        assert sensor is not None, "please provide sensor positions for consistent orientations"
+        n = xyz.shape[0]
+        # voxel size such that a 27-neighbourhood holds ~knn points
+        ext = float((xyz.max(dim=0).values - xyz.min(dim=0).values).max().item())
+        lo, hi = max(ext * 1e-5, 1e-9), max(ext, 1e-6)
+        for _ in range(20):
+            mid = math.sqrt(lo * hi)
+            if n / max(_count_voxels(xyz, mid), 1) * 9.0 > knn:     # ~9 occupied voxels of 27 on a surface
+                hi = mid
+            else:
+                lo = mid
+        h = math.sqrt(lo * hi)
+        svh = SparseFeatureHierarchy(h, 1, xyz.device).build_point_splatting(xyz)
+        base = svh.locate(xyz)[0].long()
+        centre = xyz.mean(dim=0, keepdim=True)
+        xc = xyz - centre
+        mom = torch.cat([torch.ones((n, 1), device=xyz.device), xc, (xc[:, :, None] * xc[:, None, :]).reshape(n, 9)], 1)
+        acc = torch.zeros((svh.num_voxels(0), 13), device=xyz.device, dtype=torch.float64)
+        acc.index_add_(0, base, mom.double())
+        nb = svh.nbr27[0].long()
+        agg = torch.zeros_like(acc)
+        for s in range(27):
+            idx = nb[:, s]
+            agg += torch.where((idx >= 0)[:, None], acc[idx.clamp(min=0)], torch.zeros((), dtype=acc.dtype, device=acc.device))
+        cnt = agg[:, 0:1].clamp(min=1.0)
+        mean = agg[:, 1:4] / cnt
+        cov = agg[:, 4:].reshape(-1, 3, 3) / cnt[:, :, None] - mean[:, :, None] * mean[:, None, :]
+        evals, evecs = torch.linalg.eigh(cov)
+        vox_normal = evecs[:, :, 0].float()
+        nrm = vox_normal[base]
+        view = sensor - xyz
+        view = view / (torch.linalg.norm(view, dim=-1, keepdim=True) + 1e-6)
+        cos = torch.sum(view * nrm, dim=1)
+        nrm = torch.where((cos < 0)[:, None], -nrm, nrm)
+        keep = cos.abs() > math.cos(math.radians(max_angle_deg))
+        return xyz[keep], nrm[keep], None
+
+    return fn
+
+
+class ChunkedField(BaseField):
+    """Union of independently reconstructed cubic chunks (reference semantics: serial chunk loop,
+    examples/recons_by_chunk.py:27-29).  A query is answered by the chunk whose core contains it."""
+
+    def __init__(self, fields: List[KernelField], cores: torch.Tensor, chunk_size: float):
+        super().__init__(fields[0].svh)
+        self.fields = fields
+        self.cores = cores                       # (n_chunks, 3) integer chunk coordinates
+        self.chunk_size = chunk_size
+
+    def _owner(self, xyz):
+        c = torch.floor(xyz / self.chunk_size).long()
+        owner = torch.full((xyz.shape[0],), -1, dtype=torch.long, device=xyz.device)
+        for k in range(self.cores.shape[0]):
+            owner[(c == self.cores[k].to(xyz.device)[None]).all(dim=1)] = k
+        return owner
+
+    def evaluate_f(self, xyz, grad=False):
+        owner = self._owner(xyz)
+        val = torch.zeros(xyz.shape[0], device=xyz.device)
+        g = torch.zeros((xyz.shape[0], 3), device=xyz.device) if grad else None
+        for k, f in enumerate(self.fields):
+            m = owner == k
+            if m.any():
+                r = f.evaluate_f(xyz[m].to(f.svh.device), grad=grad)
+                val[m] = r.value.to(xyz.device)
+                if grad:
+                    g[m] = r.gradient.to(xyz.device)
+        return EvaluationResult(value=val, gradient=g)
+
+    def extract_dual_mesh(self, grid_upsample: int = 1, mise_iter: int = 0, max_points: int = -1):
+        vs, fs, off = [], [], 0
+        dev = self.fields[0].svh.device
+        for k, f in enumerate(self.fields):
+            m = f.extract_dual_mesh(grid_upsample=grid_upsample, mise_iter=mise_iter, max_points=max_points)
+            if m.f.shape[0] == 0:
+                continue
+            cen = m.v[m.f].mean(dim=1)
+            inside = (torch.floor(cen / self.chunk_size).long() == self.cores[k].to(cen.device)[None]).all(dim=1)
+            tri = m.f[inside]
+            used = torch.zeros(m.v.shape[0], dtype=torch.bool, device=cen.device)
+            used[tri.reshape(-1)] = True
+            remap = torch.cumsum(used.long(), 0) - 1
+            vs.append(m.v[used].to(dev))
+            fs.append((remap[tri] + off).to(dev))
+            off += int(used.sum().item())
+        if not vs:
+            return DualMesh(v=torch.zeros((0, 3), device=dev), f=torch.zeros((0, 3), dtype=torch.int64, device=dev), c=None)
+        return DualMesh(v=torch.cat(vs), f=torch.cat(fs), c=None)
+
+    def to_(self, device):
+        for f in self.fields:
+            f.to_(device)
+        return self
+
+
+class Reconstructor:
+    def __init__(self, device, network: Optional[NKSRNetwork] = None, tree_depth: int = 4, adaptive_depth: int = 2,
+                 kernel_dim: int = 4):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.NksrError("nksr_b200.Reconstructor needs a CUDA device (B200-only build, no CPU path)")
+        _lib.load()
+        self.chunk_tmp_device = self.device
+        self.tree_depth, self.adaptive_depth = tree_depth, adaptive_depth
+        self.network = (network or NKSRNetwork(dict(kernel_dim=kernel_dim, tree_depth=tree_depth,
+                                                    adaptive_depth=adaptive_depth))).to(self.device)
+        self.last_stats = {}
+
+    # one chunk / the whole cloud: models/nksr_net.py:41-133 without the Lightning plumbing
+    def _reconstruct_one(self, xyz, normal, sensor, voxel_size, approx_kernel_grad, solver_tol, fused_mode,
+                         solver_max_iter) -> KernelField:
+        if normal is not None:
+            feat = normal
+        elif sensor is not None:
+            view = sensor - xyz
+            feat = view / (torch.linalg.norm(view, dim=-1, keepdim=True) + 1e-6)     # models/nksr_net.py:48-52
+        else:
+            raise ValueError("either normal or sensor (with a normal-estimating preprocess_fn) is required")
+        svh = SparseFeatureHierarchy(voxel_size, self.tree_depth, self.device).build_point_splatting(xyz)
+        enc = self.network.encoder(xyz, feat, svh, 0)
+        feats, dec_svh, _ = self.network.unet(enc, svh, adaptive_depth=self.adaptive_depth)
+        field = KernelField(dec_svh, self.network.interpolators, feats.basis_features, approx_kernel_grad)
+        field.solver_config["tol"] = float(solver_tol)
+        field.solver_config["max_iter"] = int(solver_max_iter)
+        ad = min(self.adaptive_depth, dec_svh.depth)
+        normal_xyz = torch.cat([dec_svh.get_voxel_centers(d) for d in range(ad)])
+        normal_value = torch.cat([feats.normal_features[d] for d in range(ad)])
+        normal_weight = NORMAL_WEIGHT / normal_xyz.shape[0] * (voxel_size ** 2)        # models/nksr_net.py:103-104
+        field.solve(xyz, normal_xyz, -normal_value, POS_WEIGHT / xyz.shape[0], normal_weight, 1.0,
+                    fused_mode=fused_mode)
+        field.set_mask_field(LayerField(dec_svh, ad))
+        return field
+
+    def reconstruct(self, xyz: torch.Tensor, normal: Optional[torch.Tensor] = None,
+                    sensor: Optional[torch.Tensor] = None, detail_level: Optional[float] = 0.0,
+                    voxel_size: Optional[float] = None, chunk_size: Optional[float] = None,
+                    preprocess_fn: Optional[Callable] = None, approx_kernel_grad: bool = False,
+                    solver_tol: float = 1.0e-5, fused_mode: bool = True, solver_max_iter: int = 2000):
+        _lib.require_cuda(xyz, "xyz")
+        xyz = xyz.detach().to(self.device, torch.float32).contiguous()
+        normal = normal.detach().to(self.device, torch.float32).contiguous() if normal is not None else None
+        sensor = sensor.detach().to(self.device, torch.float32).contiguous() if sensor is not None else None
+        if chunk_size is not None and chunk_size > 0:
+            # NKSR-USAGE.md:137: detail_level / voxel_size are not tunable in chunk mode
+            voxel_size = DEFAULT_VOXEL_SIZE
+            return self._reconstruct_chunks(xyz, normal, sensor, voxel_size, float(chunk_size), preprocess_fn,
+                                            approx_kernel_grad, solver_tol, fused_mode, solver_max_iter)
+        if preprocess_fn is not None:
+            xyz, normal, sensor = preprocess_fn(xyz, normal, sensor)
+            xyz = xyz.contiguous()
+        if voxel_size is None:
+            voxel_size = DEFAULT_VOXEL_SIZE if detail_level is None else voxel_size_from_detail(xyz, detail_level)
+        field = self._reconstruct_one(xyz, normal, sensor, float(voxel_size), approx_kernel_grad, solver_tol,
+                                      fused_mode, solver_max_iter)
+        self.last_stats = dict(field.solve_info, voxel_size=float(voxel_size), points=int(xyz.shape[0]))
+        return field
+
+    def _reconstruct_chunks(self, xyz, normal, sensor, voxel_size, chunk_size, preprocess_fn, approx_kernel_grad,
+                            solver_tol, fused_mode, solver_max_iter, chunk_filter=None):
+        margin = voxel_size * (2 ** (self.tree_depth - 1)) * 2.0       # two coarsest voxels of overlap
+        cidx = torch.floor(xyz / chunk_size).long()
+        cores = torch.unique(cidx, dim=0)
+        fields, kept = [], []
+        for k in range(cores.shape[0]):
+            if chunk_filter is not None and not chunk_filter(k, cores.shape[0]):
+                continue
+            lo = cores[k].float() * chunk_size - margin
+            hi = (cores[k].float() + 1.0) * chunk_size + margin
+            m = ((xyz >= lo[None]) & (xyz < hi[None])).all(dim=1)
+            cx = xyz[m]
+            cn = normal[m] if normal is not None else None
+            cs = sensor[m] if sensor is not None else None
+            if preprocess_fn is not None:
+                cx, cn, cs = preprocess_fn(cx, cn, cs)
+            if cx.shape[0] < 16:
+                continue
+            f = self._reconstruct_one(cx.contiguous(), cn, cs, voxel_size, approx_kernel_grad, solver_tol, fused_mode,
+                                      solver_max_iter)
+            if self.chunk_tmp_device != self.device and self.chunk_tmp_device.type == "cuda":
+                f.to_(self.chunk_tmp_device)
+            fields.append(f)
+            kept.append(cores[k])
+        if not fields:
+            raise _lib.NksrError("no chunk contained enough points")
+        return ChunkedField(fields, torch.stack(kept), chunk_size)

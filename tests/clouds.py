@@ -1,0 +1,39 @@
+"""Seeded synthetic oriented point clouds shared by the tests."""
+import numpy as np
+
+
+def sphere(n, radius=0.35, noise=0.002, seed=0, centre=(0.0, 0.0, 0.0)):
+    rng = np.random.default_rng(seed)
+    p = rng.normal(size=(n, 3))
+    p /= np.linalg.norm(p, axis=1, keepdims=True)
+    xyz = p * radius + rng.normal(size=(n, 3)) * noise + np.asarray(centre)
+    return xyz.astype(np.float32), p.astype(np.float32)
+
+
+def shapenet_like(n=3000, noise=0.005, seed=2):
+    """cfg2: sphere r=.35 U torus R=.3 r=.1 U box .5^3 surfaces (area weighted), noisy."""
+    rng = np.random.default_rng(seed)
+    areas = np.array([4 * np.pi * 0.35 ** 2, 4 * np.pi ** 2 * 0.3 * 0.1, 6 * 0.25])
+    cnt = rng.multinomial(n, areas / areas.sum())
+    pts, nrm = [], []
+    p = rng.normal(size=(cnt[0], 3)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+    pts.append(p * 0.35); nrm.append(p)
+    u, v = rng.uniform(0, 2 * np.pi, cnt[1]), rng.uniform(0, 2 * np.pi, cnt[1])
+    pts.append(np.stack([(0.3 + 0.1 * np.cos(v)) * np.cos(u), (0.3 + 0.1 * np.cos(v)) * np.sin(u), 0.1 * np.sin(v)], 1))
+    nrm.append(np.stack([np.cos(v) * np.cos(u), np.cos(v) * np.sin(u), np.sin(v)], 1))
+    face = rng.integers(0, 6, cnt[2]); ab = rng.uniform(-0.25, 0.25, (cnt[2], 2))
+    q = np.zeros((cnt[2], 3)); m = np.zeros((cnt[2], 3))
+    for f in range(6):
+        s = face == f; ax = f // 2; sg = 1.0 if f % 2 else -1.0
+        q[s, ax] = 0.25 * sg; q[s, (ax + 1) % 3] = ab[s, 0]; q[s, (ax + 2) % 3] = ab[s, 1]; m[s, ax] = sg
+    pts.append(q); nrm.append(m)
+    xyz = np.concatenate(pts) + rng.normal(size=(n, 3)) * noise
+    return xyz.astype(np.float32), np.concatenate(nrm).astype(np.float32)
+
+
+def offset_blob(n, seed=5, scale=3.0, shift=(-17.3, 41.9, -5.25)):
+    """random smooth blob far from the origin with negative coordinates (range / sign tests)."""
+    rng = np.random.default_rng(seed)
+    p = rng.normal(size=(n, 3)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+    r = 1.0 + 0.2 * np.sin(3 * p[:, 0]) * np.cos(2 * p[:, 1])
+    return (p * r[:, None] * scale + np.asarray(shift)).astype(np.float32), p.astype(np.float32)

@@ -1,0 +1,252 @@
+"""GPU parity tests: every CUDA stage, called through the C-ABI (nksr_b200._lib), against the CPU
+oracle on the same seeded inputs.  Integer work bit-exact; floating point within the stated
+tolerances (fp32 kernels vs fp64 oracle)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import nksr_oracle as O
+from tests import clouds
+
+pytestmark = pytest.mark.gpu
+
+RTOL_ROW = 2e-4       # kernel rows / field values: fp32 products of ~6 factors
+RTOL_GRAM = 5e-4      # Gram entries: sums of a few hundred such products
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _build(cuda, xyz, W, L):
+    import nksr_b200
+    svh = nksr_b200.SparseFeatureHierarchy(W, L, cuda).build_point_splatting(torch.from_numpy(xyz).to(cuda))
+    osvh = O.OracleSVH(W, L).build_point_splatting(xyz)
+    return svh, osvh
+
+
+@pytest.mark.parametrize("cloud,W,L", [("shapenet", 0.02, 4), ("blob", 0.1, 4), ("sphere", 0.05, 3), ("blob", 0.37, 2)])
+def test_svh_bit_exact(cuda, cloud, W, L):
+    xyz = {"shapenet": clouds.shapenet_like(3000)[0], "blob": clouds.offset_blob(20000)[0],
+           "sphere": clouds.sphere(5000)[0]}[cloud]
+    svh, osvh = _build(cuda, xyz, W, L)
+    for l in range(L):
+        assert np.array_equal(_np(svh.keys[l]), osvh.keys[l]), f"keys level {l}"
+        assert np.array_equal(_np(svh.grids[l].active_grid_coords()), osvh.ijk(l))
+        assert np.array_equal(_np(svh.nbr27[l]).astype(np.int64), osvh.nbr27(l)), f"nbr27 level {l}"
+        cen = _np(svh.get_voxel_centers(l))
+        assert np.allclose(cen, osvh.centers(l), rtol=1e-6, atol=1e-7)
+    for l in range(L - 1):
+        par = osvh.lookup(l + 1, osvh.ijk(l).astype(np.int64) >> 1)
+        assert np.array_equal(_np(svh.parent[l]).astype(np.int64), par)
+        ch = _np(svh.child8[l + 1])
+        for i in np.random.default_rng(0).integers(0, osvh.n(l), 200):
+            slot = int(osvh.keys[l][i] & 7)
+            assert ch[par[i], slot] == i
+    q = (xyz[:4000] + np.float32(0.5 * W)).astype(np.float32)
+    assert np.array_equal(_np(svh.locate(torch.from_numpy(q).to(cuda))).astype(np.int64), osvh.locate(q))
+
+
+def test_svh_empty_and_single_point(cuda):
+    import nksr_b200
+    svh = nksr_b200.SparseFeatureHierarchy(0.1, 4, cuda).build_point_splatting(torch.zeros((0, 3), device=cuda))
+    assert all(g is None for g in svh.grids)
+    one = np.array([[0.123, -4.5, 7.7]], np.float32)
+    svh, osvh = _build(cuda, one, 0.1, 4)
+    for l in range(4):
+        assert svh.num_voxels(l) == 8 and np.array_equal(_np(svh.keys[l]), osvh.keys[l])
+    with pytest.raises(RuntimeError):
+        nksr_b200.SparseFeatureHierarchy(1e-9, 4, cuda).build_point_splatting(torch.ones((4, 3), device=cuda))
+
+
+def _feats(osvh, C, seed):
+    rng = np.random.default_rng(seed)
+    return [(0.5 + 0.2 * rng.normal(size=(osvh.n(l), C))).astype(np.float32) for l in range(osvh.depth)]
+
+
+def _field(cuda, svh, feats, approx=False):
+    import nksr_b200
+    return nksr_b200.KernelField(svh, None, [torch.from_numpy(f).to(cuda) for f in feats], approx)
+
+
+@pytest.mark.parametrize("C,approx", [(4, False), (16, False), (4, True), (3, False)])
+def test_kernel_rows_match_oracle(cuda, C, approx):
+    xyz, _ = clouds.shapenet_like(3000)
+    svh, osvh = _build(cuda, xyz, 0.02, 4)
+    feats = _feats(osvh, C, 7)
+    field = _field(cuda, svh, feats, approx)
+    q = torch.from_numpy(xyz[:1500]).to(cuda)
+    for mode in (0, 1):
+        xs, _, base, _, e = field._sorted_rows(q, mode)
+        xs_np, base_np, e_np = _np(xs), _np(base).astype(np.int64), _np(e)
+        assert np.array_equal(base_np, osvh.locate(xs_np))
+        for l in range(4):
+            nbr, K, dK = O.level_rows(osvh, l, xs_np, base_np[l], feats[l], mode == 1, approx)
+            if mode == 0:
+                got, ref = e_np[l][:, :27], K
+            else:
+                got, ref = e_np[l].reshape(-1, 3, 32)[:, :, :27], dK
+            scale = np.abs(ref).max()
+            assert np.abs(got - ref).max() <= RTOL_ROW * scale, (mode, l)
+            assert np.all(e_np[l].reshape(-1, 32)[:, 27:] == 0)
+
+
+def _solve_setup(cuda, C=4, approx=False, n_pts=3000, W=0.02, L=4, cloud="shapenet"):
+    xyz, nrm = clouds.shapenet_like(n_pts) if cloud == "shapenet" else clouds.sphere(n_pts)
+    svh, osvh = _build(cuda, xyz, W, L)
+    feats = _feats(osvh, C, 11)
+    field = _field(cuda, svh, feats, approx)
+    nxyz = np.concatenate([osvh.centers(0), osvh.centers(1)])
+    rng = np.random.default_rng(3)
+    nval = rng.normal(size=nxyz.shape).astype(np.float32)
+    nval /= np.linalg.norm(nval, axis=1, keepdims=True)
+    pw, nw, rw = 1e4 / xyz.shape[0], 1e4 / nxyz.shape[0] * W * W, 1.0
+    return field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw)
+
+
+def _gpu_csr(field):
+    s = field.system
+    n = s.rowptr.numel() - 1
+    return sp.csr_matrix((_np(s.val).astype(np.float64), _np(s.col), _np(s.rowptr)), shape=(n, n))
+
+
+@pytest.mark.parametrize("C,approx", [(4, False), (16, True)])
+def test_gram_assembly_matches_oracle(cuda, C, approx):
+    field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda, C, approx)
+    field.solver_config.update(keep_system=True, max_iter=0)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    field.solve(t(xyz), t(nxyz), t(nval), pw, nw, rw)
+    A_ref, b_ref, _ = O.build_system(osvh, feats, xyz, nxyz, nval, pw, nw, rw, approx)
+    A = _gpu_csr(field)
+    # structure: exactly the structural pattern of SPEC S6, no duplicates, sorted transposed segments
+    P = O.structural_pattern(osvh)
+    Ab = A.copy(); Ab.data[:] = 1
+    assert A.nnz == P.nnz
+    Ab.sum_duplicates()
+    assert Ab.nnz == P.nnz and (Ab - P).count_nonzero() == 0
+    # values
+    scale = abs(A_ref).max()
+    assert abs(A - A_ref).max() <= RTOL_GRAM * scale
+    assert abs(A - A.T).max() <= 1e-6 * scale          # transposed copies are bitwise copies
+    assert np.abs(_np(field.system.rhs) - b_ref).max() <= RTOL_GRAM * np.abs(b_ref).max()
+    assert np.abs(_np(field.system.diag) - A_ref.diagonal()).max() <= RTOL_GRAM * scale
+
+
+def test_gram_position_only_and_determinism(cuda):
+    field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda, 4, False, 2000, 0.05, 3, "sphere")
+    field.solver_config.update(keep_system=True, max_iter=0)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    field.solve(t(xyz), None, None, pw, 0.0, rw)
+    A1 = (_np(field.system.val).copy(), _np(field.system.col).copy())
+    A_ref, b_ref, _ = O.build_system(osvh, feats, xyz, np.zeros((0, 3), np.float32), np.zeros((0, 3)), pw, 0.0, rw)
+    assert abs(_gpu_csr(field) - A_ref).max() <= RTOL_GRAM * abs(A_ref).max()
+    field.solve(t(xyz), None, None, pw, 0.0, rw)
+    assert np.array_equal(A1[0], _np(field.system.val)) and np.array_equal(A1[1], _np(field.system.col))
+
+
+def test_spmv_and_pcg_match_oracle(cuda):
+    import nksr_b200._lib as L
+    field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda)
+    nval = -(nxyz / np.linalg.norm(nxyz, axis=1, keepdims=True)).astype(np.float32)
+    field.solver_config.update(keep_system=True, tol=1e-6, max_iter=3000, check_every=1)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    field.solve(t(xyz), t(nxyz), t(nval), pw, nw, rw)
+    A = _gpu_csr(field)
+    s = field.system
+    x = torch.randn(A.shape[0], device=cuda)
+    y = torch.empty_like(x)
+    L.call("nksr_spmv", s.rowptr, s.col, s.val, x, y, A.shape[0], L.stream_ptr(cuda))
+    yr = A @ _np(x).astype(np.float64)
+    assert np.abs(_np(y) - yr).max() <= 1e-5 * np.abs(yr).max()
+    # PCG: converged, and the solution solves the oracle's system
+    assert field.solve_info["relative_residual"] <= 1e-6
+    A_ref, b_ref, _ = O.build_system(osvh, feats, xyz, nxyz, nval, pw, nw, rw)
+    xo, it, res = O.pcg(A_ref, b_ref, 1e-9, 5000)
+    alpha = _np(field.alpha).astype(np.float64)
+    assert np.linalg.norm(A_ref @ alpha - b_ref) <= 1e-4 * np.linalg.norm(b_ref)
+    # same field: compare f at the points rather than alpha (ill-conditioned directions)
+    fo = O.evaluate_f(osvh, feats, xo, xyz[:500])
+    fg = _np(field.evaluate_f(t(xyz[:500])).value)
+    assert np.abs(fo - fg).max() <= 2e-3 * max(np.abs(fo).max(), 1e-3) + 2e-4
+    assert abs(field.solve_info["iterations"] - O.pcg(A_ref, b_ref, 1e-6, 5000, dtype=np.float32)[1]) <= \
+        0.25 * field.solve_info["iterations"] + 5
+
+
+@pytest.mark.parametrize("C,approx", [(4, False), (16, True)])
+def test_evaluate_matches_oracle(cuda, C, approx):
+    xyz, _ = clouds.shapenet_like(3000)
+    svh, osvh = _build(cuda, xyz, 0.02, 4)
+    feats = _feats(osvh, C, 5)
+    field = _field(cuda, svh, feats, approx)
+    rng = np.random.default_rng(1)
+    alpha = rng.normal(size=osvh.offsets()[-1]).astype(np.float32)
+    field.alpha = torch.from_numpy(alpha).to(cuda)
+    q = np.concatenate([xyz[:1000] + rng.normal(size=(1000, 3)).astype(np.float32) * 0.01,
+                        rng.uniform(-0.7, 0.7, size=(500, 3)).astype(np.float32),       # mostly outside the band
+                        osvh.centers(0)[:300], osvh.centers(2)[:100]]).astype(np.float32)
+    r = field.evaluate_f(torch.from_numpy(q).to(cuda), grad=True)
+    fo, go = O.evaluate_f(osvh, feats, alpha.astype(np.float64), q, grad=True, approx_kernel_grad=approx)
+    assert np.abs(_np(r.value) - fo).max() <= RTOL_ROW * np.abs(fo).max() * 10
+    assert np.abs(_np(r.gradient) - go).max() <= RTOL_ROW * np.abs(go).max() * 10
+    r2 = field.evaluate_f(torch.from_numpy(q).to(cuda))
+    assert np.array_equal(_np(r2.value), _np(r.value))
+
+
+@pytest.mark.parametrize("g,mise", [(1, 0), (2, 0), (1, 1), (1, 2), (2, 1)])
+def test_dual_mesh_matches_oracle(cuda, g, mise):
+    """Same field values on both sides (the oracle's MC driver calls the GPU evaluator), so the
+    topology must agree exactly and the vertices to float tolerance."""
+    field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda, 4, False, 4000, 0.05, 3, "sphere")
+    nval = -(nxyz / np.linalg.norm(nxyz, axis=1, keepdims=True)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    field.solve(t(xyz), t(nxyz), t(nval), pw, nw, rw)
+    mesh = field.extract_dual_mesh(grid_upsample=g, mise_iter=mise)
+    vo, fo = O.extract_dual_mesh(osvh, lambda q: _np(field.evaluate_f(t(q.astype(np.float32))).value), g, mise)
+    assert mesh.f.shape[0] == fo.shape[0] and mesh.v.shape[0] == vo.shape[0] and fo.shape[0] > 100
+    assert np.array_equal(_np(mesh.f), fo)
+    assert np.abs(_np(mesh.v) - vo).max() <= 1e-5
+    # closed where sampled, outward oriented
+    v, f = _np(mesh.v).astype(np.float64), _np(mesh.f)
+    nrm = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    assert (np.sum(nrm * v[f].mean(1), axis=1) > 0).mean() > 0.99
+    # max_points batching does not change the result
+    mesh2 = field.extract_dual_mesh(grid_upsample=g, mise_iter=mise, max_points=1000)
+    assert torch.equal(mesh2.f, mesh.f) and torch.equal(mesh2.v, mesh.v)
+
+
+def test_mask_trimming_matches_oracle(cuda):
+    import nksr_b200
+    field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda, 4, False, 4000, 0.05, 3, "sphere")
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    field.solve(t(xyz), t(nxyz), t(nval), pw, nw, rw)        # random normals: spurious sheets exist
+    field.set_mask_field(nksr_b200.LayerField(svh, 1))
+    mesh = field.extract_dual_mesh(mise_iter=1)
+
+    def mask(v):
+        return osvh.locate(v.astype(np.float32))[0] >= 0
+    vo, fo = O.extract_dual_mesh(osvh, lambda q: _np(field.evaluate_f(t(q.astype(np.float32))).value), 1, 1, mask)
+    assert np.array_equal(_np(mesh.f), fo) and np.abs(_np(mesh.v) - vo).max() <= 1e-5
+
+
+def test_reconstructor_end_to_end_sphere(cuda):
+    import nksr_b200
+    xyz, nrm = clouds.sphere(40000, noise=0.001)
+    rec = nksr_b200.Reconstructor(cuda)
+    field = rec.reconstruct(torch.from_numpy(xyz).to(cuda), torch.from_numpy(nrm).to(cuda), voxel_size=0.02)
+    mesh = field.extract_dual_mesh(mise_iter=1)
+    r = np.linalg.norm(_np(mesh.v), axis=1)
+    assert mesh.f.shape[0] > 1000
+    assert abs(np.median(r) - 0.35) < 0.004 and np.percentile(np.abs(r - 0.35), 99) < 0.02
+    res = field.evaluate_f(torch.from_numpy(xyz[:1000]).to(cuda), grad=True)
+    assert res.value.abs().mean().item() < 5e-3
+    g = _np(res.gradient)
+    assert np.mean(np.sum(-g / (np.linalg.norm(g, axis=1, keepdims=True) + 1e-9) * nrm[:1000], axis=1)) > 0.9
+    # detail_level path and chunked path run
+    f2 = rec.reconstruct(torch.from_numpy(xyz).to(cuda), torch.from_numpy(nrm).to(cuda), detail_level=0.5)
+    assert f2.extract_dual_mesh().f.shape[0] > 100
+    f3 = rec.reconstruct(torch.from_numpy(xyz * 10).to(cuda), torch.from_numpy(nrm).to(cuda), detail_level=None,
+                         chunk_size=4.0)
+    m3 = f3.extract_dual_mesh()
+    r3 = np.linalg.norm(_np(m3.v), axis=1)
+    assert m3.f.shape[0] > 500 and abs(np.median(r3) - 3.5) < 0.05
