@@ -128,11 +128,13 @@ NKSR_API int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, co
 NKSR_API int nksr_spmv(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
               float* y, int64_t n, void* stream);
 NKSR_API size_t nksr_pcg_workspace_bytes(int64_t n);
-/* Jacobi-PCG from x=0. info[0]=iterations, info[1]=relative residual (host doubles). */
+/* Jacobi-PCG from x=0. info (host double[4]): [0]=iterations, [1]=relative residual; with
+ * profile != 0 also [2]=total ms of the SpMV launches (CUDA events on `stream`, first 512
+ * iterations) and [3]=number of launches timed. */
 NKSR_API int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val,
                    const float* diag, const float* b, float* x, int64_t n, float tol,
-                   int max_iter, int check_every, void* ws, size_t ws_bytes, double* info,
-                   void* stream);
+                   int max_iter, int check_every, int profile, void* ws, size_t ws_bytes,
+                   double* info, void* stream);
 
 /* ---- a5: field.evaluate_f (models/loss.py:189-198,225) ---- */
 NKSR_API int nksr_evaluate(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* alpha,

@@ -64,7 +64,7 @@ _SIGNATURES = {
     "nksr_gram_sort_down": ("i", "pppqqippp"),
     "nksr_spmv": ("i", "pppppqp"),
     "nksr_pcg_workspace_bytes": ("z", "q"),
-    "nksr_pcg_solve": ("i", "pppppp" + "qfii" + "pzdp"),
+    "nksr_pcg_solve": ("i", "pppppp" + "qfiii" + "pzdp"),
     "nksr_evaluate": ("i", "SFppqiippp"),
     "nksr_mesh_cell_flags": ("i", "Spp"),
     "nksr_mesh_stage0_cells": ("i", "Sppipp"),

@@ -11,24 +11,30 @@ struct LaneKernel {
 };
 
 // weights of neighbour d in {-1,0,1} along one axis at local coordinate tau in [-.5,.5)
+// Tent derivative (SPEC S4): one-sided derivative of the trilinear cell containing x, except in
+// the snap zone |tau| < 2^-12 around a voxel centre, where the symmetric derivative is used --
+// the reference places its normal constraints exactly AT voxel centres (models/nksr_net.py:100),
+// where a one-sided rule would depend on the last rounding bit of the coordinate.
+#define NKSR_TENT_SNAP 0.000244140625f
 __device__ __forceinline__ void axis_weights(float tau, int d, float& b, float& db, float& t, float& dt) {
+  const bool mid = fabsf(tau) < NKSR_TENT_SNAP;
   if (d == 0) {
     b = 0.75f - tau * tau;
     db = -2.f * tau;
     t = tau >= 0.f ? 1.f - tau : 1.f + tau;
-    dt = tau >= 0.f ? -1.f : 1.f;
+    dt = mid ? 0.f : (tau >= 0.f ? -1.f : 1.f);
   } else if (d < 0) {
     float h = 0.5f - tau;
     b = 0.5f * h * h;
     db = -h;
     t = tau >= 0.f ? 0.f : -tau;
-    dt = tau >= 0.f ? 0.f : -1.f;
+    dt = mid ? -0.5f : (tau >= 0.f ? 0.f : -1.f);
   } else {
     float h = 0.5f + tau;
     b = 0.5f * h * h;
     db = h;
     t = tau >= 0.f ? tau : 0.f;
-    dt = tau >= 0.f ? 1.f : 0.f;
+    dt = mid ? 0.5f : (tau >= 0.f ? 1.f : 0.f);
   }
 }
 

@@ -174,14 +174,20 @@ size_t nksr_pcg_workspace_bytes(int64_t n) {
 }
 
 int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag, const float* b,
-                   float* x, int64_t n, float tol, int max_iter, int check_every, void* ws, size_t ws_bytes,
-                   double* info, void* stream) {
+                   float* x, int64_t n, float tol, int max_iter, int check_every, int profile, void* ws,
+                   size_t ws_bytes, double* info, void* stream) {
   if (n <= 0 || !info || max_iter < 0) return NKSR_E_INVALID;
   if (ws_bytes < nksr_pcg_workspace_bytes(n)) return NKSR_E_WORKSPACE;
   if (check_every < 1) check_every = 1;
   cudaStream_t s = as_stream(stream);
   PcgWs w = carve(ws, n);
   double host_part[kGrid];
+  // optional profiling: CUDA events around every SpMV launch on this stream (info[2], info[3])
+  const int kMaxEv = 512;
+  cudaEvent_t ev[2 * kMaxEv];
+  int n_ev = 0;
+  if (profile)
+    for (int i = 0; i < 2 * kMaxEv; ++i) cudaEventCreate(&ev[i]);
   // all partial arrays start at zero (blocks beyond a short grid never write)
   if (cudaMemsetAsync(w.rz0, 0, 5 * align256(kGrid * sizeof(double)), s) != cudaSuccess) return NKSR_E_CUDA;
   k_pcg_init<<<kGrid, kBlock, 0, s>>>(b, diag, x, w.r, w.p, n, w.rz0, w.bb);
@@ -193,14 +199,21 @@ int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val, 
   for (int i = 0; i < kGrid; ++i) bb += host_part[i];
   info[0] = 0.0;
   info[1] = 0.0;
-  if (!(bb > 0.0)) return NKSR_OK;
+  if (profile) { info[2] = 0.0; info[3] = 0.0; }
+  if (!(bb > 0.0)) {
+    if (profile) for (int i = 0; i < 2 * kMaxEv; ++i) cudaEventDestroy(ev[i]);
+    return NKSR_OK;
+  }
   const double target = (double)tol * (double)tol * bb;
   double* rz_cur = w.rz0;
   double* rz_new = w.rz1;
   int it = 0;
   double rr = bb;
   while (it < max_iter) {
+    const bool timed = profile && n_ev < kMaxEv;
+    if (timed) cudaEventRecord(ev[2 * n_ev], s);
     k_spmv<true><<<kGrid, kBlock, 0, s>>>(rowptr, col, val, w.p, w.ap, n, w.pap);
+    if (timed) { cudaEventRecord(ev[2 * n_ev + 1], s); ++n_ev; }
     k_pcg_update<<<kGrid, kBlock, 0, s>>>(diag, w.p, w.ap, x, w.r, n, rz_cur, w.pap, rz_new, w.rr);
     k_pcg_direction<<<kGrid, kBlock, 0, s>>>(w.ap, w.p, n, rz_cur, rz_new);
     double* t = rz_cur; rz_cur = rz_new; rz_new = t;
@@ -218,6 +231,18 @@ int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val, 
   NKSR_CHECK_LAUNCH();
   info[0] = (double)it;
   info[1] = sqrt(rr / bb);
+  if (profile) {
+    cudaStreamSynchronize(s);
+    double ms = 0.0;
+    for (int i = 0; i < n_ev; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+      ms += t;
+    }
+    info[2] = ms;
+    info[3] = (double)n_ev;
+    for (int i = 0; i < 2 * kMaxEv; ++i) cudaEventDestroy(ev[i]);
+  }
   return NKSR_OK;
 }
 

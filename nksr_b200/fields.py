@@ -204,11 +204,14 @@ class KernelField(BaseField):
         alpha = torch.empty(n, dtype=torch.float32, device=dev)
         nb = call("nksr_pcg_workspace_bytes", n)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-        info = (C.c_double * 2)()
+        info = (C.c_double * 4)()
+        profile = int(bool(self.solver_config.get("profile")))
         call("nksr_pcg_solve", rowptr, col, val, diag, rhs, alpha, n, float(self.solver_config["tol"]),
-             int(self.solver_config["max_iter"]), int(self.solver_config["check_every"]), ws, nb, info, st)
+             int(self.solver_config["max_iter"]), int(self.solver_config["check_every"]), profile, ws, nb, info, st)
         self.alpha = alpha
         self.solve_info = {"iterations": int(info[0]), "relative_residual": float(info[1]), "n": n, "nnz": nnz}
+        if profile:
+            self.solve_info.update(spmv_ms=float(info[2]), spmv_launches=int(info[3]))
         if self.solver_config.get("verbose"):
             print(f"[nksr_b200] PCG: n={n} nnz={nnz} iters={int(info[0])} relres={float(info[1]):.3e}")
         if self.solver_config.get("keep_system"):

@@ -28,6 +28,7 @@ import scipy.sparse as sp
 MAX_DEPTH = 8
 KEY_BITS = 21
 HALF_OFFSET = 1 << 20          # offset of half-voxel coordinates (|h| < 2^20)
+TENT_SNAP = 2.0 ** -12         # snap zone of the tent derivative around voxel centres
 
 
 # --------------------------------------------------------------------------- keys
@@ -167,10 +168,15 @@ def _bspline(tau):
 
 
 def _tent(tau):
-    """trilinear (tent) weights of d=-1,0,+1; right-derivative at the kink (SPEC S4)."""
+    """trilinear (tent) weights of d=-1,0,+1 (SPEC S4).  Derivative: one-sided (the trilinear
+    cell containing x) except in the snap zone |tau| < 2^-12 around a voxel centre, where the
+    symmetric derivative (-1/2, 0, +1/2) is used: the reference puts its normal constraints
+    exactly at voxel centres (models/nksr_net.py:100)."""
     pos = tau >= 0
+    mid = np.abs(tau) < TENT_SNAP
     w = np.stack([np.where(pos, 0.0, -tau), np.where(pos, 1.0 - tau, 1.0 + tau), np.where(pos, tau, 0.0)], axis=-1)
-    dw = np.stack([np.where(pos, 0.0, -1.0), np.where(pos, -1.0, 1.0), np.where(pos, 1.0, 0.0)], axis=-1)
+    dw = np.stack([np.where(mid, -0.5, np.where(pos, 0.0, -1.0)), np.where(mid, 0.0, np.where(pos, -1.0, 1.0)),
+                   np.where(mid, 0.5, np.where(pos, 1.0, 0.0))], axis=-1)
     return w, dw
 
 
