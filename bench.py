@@ -1,0 +1,407 @@
+"""bench.py -- points/sec of reconstruct() on the BASELINE.json workload, with roofline evidence.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+  python bench.py --impl reference ...                      CPU arm: the oracle port on host cores
+
+A "step" is one `Reconstructor.reconstruct()` of one synthetic oriented cloud (SVH build ->
+network stand-in -> kernel rows -> Gram assembly -> PCG).  `value` times it with the inputs
+already resident in HBM; `e2e` times the same call from pinned HOST buffers (H2D of xyz+sensor
+inside the timed region, D2H of the solved coefficients).  N > 1: every rank reconstructs its
+own tile of the scene (independent spatial chunks, no data-path collective) -> weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[3]: outdoor / CARLA-style cloud, voxel 0.1, sensor feature
+    "cfg4_outdoor_10M": dict(points=10_000_000, voxel_size=0.1, kind="outdoor"),
+    # configs[2]: indoor scene 1M points, voxel 0.02
+    "cfg3_indoor_1M": dict(points=1_000_000, voxel_size=0.02, kind="indoor"),
+    "dev_outdoor_1M": dict(points=1_000_000, voxel_size=0.1, kind="outdoor"),
+}
+SOLVER = dict(approx_kernel_grad=True, solver_tol=1e-4, fused_mode=True)     # examples/recons_waymo.py:33
+
+
+# ----------------------------------------------------------------------------- synthetic scenes
+def make_outdoor(n, seed, device, tile=0):
+    """200 x 200 m ground height-field + 60 building boxes, LiDAR-like 1/r density about a 200 m
+    sensor polyline.  Returns xyz, sensor (float32, on `device`)."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    n_g = int(n * 0.72)
+    n_b = n - n_g
+    u = torch.rand(n_g, generator=g)
+    y0 = 4.0
+    ay = y0 * ((1.0 + 100.0 / y0) ** u - 1.0)                       # density ~ 1/(|y|+y0)
+    y = ay * (torch.randint(0, 2, (n_g,), generator=g) * 2 - 1).float()
+    x = torch.rand(n_g, generator=g) * 200.0 - 100.0
+    z = 0.8 * torch.sin(x / 15.0) * torch.cos(y / 11.0) + 0.3 * torch.sin(x / 4.0 + y / 5.0)
+    ground = torch.stack([x, y, z], 1)
+    # buildings
+    gb = torch.Generator(device="cpu").manual_seed(1234)            # same city for every tile / seed
+    nb = 60
+    bx = torch.rand(nb, generator=gb) * 180.0 - 90.0
+    by = (torch.rand(nb, generator=gb) * 75.0 + 10.0) * (torch.randint(0, 2, (nb,), generator=gb) * 2 - 1).float()
+    sx = torch.rand(nb, generator=gb) * 12.0 + 8.0
+    sy = torch.rand(nb, generator=gb) * 12.0 + 8.0
+    sz = torch.rand(nb, generator=gb) * 19.0 + 6.0
+    wgt = (2 * (sx + sy) * sz + sx * sy) / (by.abs() + 5.0)
+    which = torch.multinomial(wgt / wgt.sum(), n_b, replacement=True, generator=g)
+    face_area = torch.stack([sy * sz, sy * sz, sx * sz, sx * sz, sx * sy], 1)[which]
+    face = torch.multinomial(face_area / face_area.sum(1, keepdim=True), 1, generator=g).squeeze(1)
+    a, b = torch.rand(n_b, generator=g), torch.rand(n_b, generator=g)
+    cx, cy, hx, hy, hz = bx[which], by[which], sx[which] / 2, sy[which] / 2, sz[which]
+    px = torch.where(face == 0, cx - hx, torch.where(face == 1, cx + hx, cx + (2 * a - 1) * hx))
+    py = torch.where(face < 2, cy + (2 * a - 1) * hy, torch.where(face == 2, cy - hy, torch.where(face == 3, cy + hy, cy + (2 * b - 1) * hy)))
+    pz = torch.where(face < 4, b * hz, hz)
+    build = torch.stack([px, py, pz], 1)
+    xyz = torch.cat([ground, build])
+    sensor = torch.stack([xyz[:, 0].clamp(-100, 100), torch.zeros(n), torch.full((n,), 12.0)], 1)
+    sensor = sensor + 0.05 * torch.randn(n, 3, generator=g)
+    ray = xyz - sensor
+    xyz = xyz + ray / ray.norm(dim=1, keepdim=True) * (0.02 * torch.randn(n, 1, generator=g))
+    xyz[:, 0] += 200.0 * tile                                       # tiles along the path (cfg5)
+    sensor[:, 0] += 200.0 * tile
+    perm = torch.randperm(n, generator=g)
+    return xyz[perm].float().contiguous(), sensor[perm].float().contiguous()
+
+
+def make_indoor(n, seed, device, tile=0):
+    """8 x 6 x 3 m room shell + 20 boxes, uniform by area, noise 0.25 W (cfg3).  Sensor = room centre."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dims = torch.tensor([8.0, 6.0, 3.0])
+    gb = torch.Generator(device="cpu").manual_seed(4321)
+    nb = 20
+    bc = torch.rand(nb, 3, generator=gb) * torch.tensor([6.0, 4.0, 0.0]) + torch.tensor([1.0, 1.0, 0.0])
+    bs = torch.rand(nb, 3, generator=gb) * torch.tensor([1.2, 1.2, 1.5]) + 0.4
+    boxes_lo = torch.cat([torch.zeros(1, 3), torch.stack([bc[:, 0] - bs[:, 0] / 2, bc[:, 1] - bs[:, 1] / 2, torch.zeros(nb)], 1)])
+    boxes_hi = torch.cat([dims[None], torch.stack([bc[:, 0] + bs[:, 0] / 2, bc[:, 1] + bs[:, 1] / 2, bs[:, 2]], 1)])
+    ext = boxes_hi - boxes_lo
+    areas = torch.stack([ext[:, 1] * ext[:, 2], ext[:, 1] * ext[:, 2], ext[:, 0] * ext[:, 2], ext[:, 0] * ext[:, 2],
+                         ext[:, 0] * ext[:, 1], ext[:, 0] * ext[:, 1]], 1)
+    flat = areas.reshape(-1)
+    pick = torch.multinomial(flat / flat.sum(), n, replacement=True, generator=g)
+    box, face = pick // 6, pick % 6
+    uv = torch.rand(n, 2, generator=g)
+    ax = face // 2
+    side = (face % 2).float()
+    p = torch.zeros(n, 3)
+    lo, e = boxes_lo[box], ext[box]
+    for a in range(3):
+        m = ax == a
+        o1, o2 = (a + 1) % 3, (a + 2) % 3
+        p[m, a] = lo[m, a] + side[m] * e[m, a]
+        p[m, o1] = lo[m, o1] + uv[m, 0] * e[m, o1]
+        p[m, o2] = lo[m, o2] + uv[m, 1] * e[m, o2]
+    p = p + 0.005 * torch.randn(n, 3, generator=g)
+    sensor = torch.tensor([4.0, 3.0, 1.5]).expand(n, 3).clone()
+    p[:, 0] += 10.0 * tile
+    sensor[:, 0] += 10.0 * tile
+    return p.float().contiguous(), sensor.float().contiguous()
+
+
+def make_cloud(workload, seed, tile=0, points=None):
+    cfg = WORKLOADS[workload]
+    n = points or cfg["points"]
+    fn = make_outdoor if cfg["kind"] == "outdoor" else make_indoor
+    return fn(n, seed, "cpu", tile)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def _cpu_reconstruct_chunk(args):
+    """One independent spatial crop reconstructed by the numpy/scipy oracle (single thread)."""
+    import numpy as np
+    from oracle import nksr_oracle as O
+    xyz, nrm, W, L = args
+    t0 = time.perf_counter()
+    svh = O.OracleSVH(W, L).build_point_splatting(xyz)
+    feats = [np.full((svh.n(l), 4), 0.5, np.float32) for l in range(L)]
+    nxyz = np.concatenate([svh.centers(0), svh.centers(1)])
+    base = svh.locate(nxyz)          # stand-in normals: nearest input normal is not needed for timing
+    nval = np.tile(np.array([[0.0, 0.0, -1.0]], np.float32), (nxyz.shape[0], 1))
+    A, b, _ = O.build_system(svh, feats, xyz, nxyz, nval, 1e4 / xyz.shape[0], 1e4 / nxyz.shape[0] * W * W, 1.0, True)
+    x, it, res = O.pcg(A, b, 1e-4, 2000, dtype=np.float32)
+    return xyz.shape[0], time.perf_counter() - t0, it, int(A.nnz), int(A.shape[0])
+
+
+def cpu_baseline(workload, sample_points, cores, seed=4):
+    """Times the CPU restatement (oracle port) on `cores` processes, each reconstructing one spatial
+    crop of the same synthetic scene (crops keep the scene's local density).  Returns points/sec."""
+    import multiprocessing as mp
+    import numpy as np
+    cfg = WORKLOADS[workload]
+    xyz, sensor = make_cloud(workload, seed, 0, points=min(cfg["points"], 2_000_000))
+    xyz = xyz.numpy()
+    W = cfg["voxel_size"]
+    per = max(sample_points // cores, 2000)
+    # crops: nearest `per` points (in x-y) around seeded anchor points
+    rng = np.random.default_rng(seed)
+    jobs = []
+    for a in rng.choice(xyz.shape[0], cores, replace=False):
+        d = np.abs(xyz[:, :2] - xyz[a, :2]).max(axis=1)
+        idx = np.argpartition(d, per)[:per]
+        jobs.append((xyz[idx].copy(), None, W, 4))
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        out = pool.map(_cpu_reconstruct_chunk, jobs)
+    wall = time.perf_counter() - t0
+    pts = sum(o[0] for o in out)
+    return pts / wall, pts, wall, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workload = args.workload
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, pts, wall, out = cpu_baseline(workload, args.cpu_sample, cores, seed=4 + s)
+        if s >= args.warmup:
+            vals.append((v, pts, wall))
+    v = sum(p for _, p, _ in vals) / sum(w for _, _, w in vals)
+    sample = f"{cores} spatial crops x {vals[0][1] // cores} points of {workload} per step (numpy/scipy oracle, 1 process per core)"
+    line = {"impl": "reference", "metric": "points/sec reconstruct()", "value": v, "unit": "points/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(w for _, _, w in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "voxel_size": WORKLOADS[workload]["voxel_size"], "tree_depth": 4},
+            "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg4_outdoor_10M", choices=sorted(WORKLOADS))
+    ap.add_argument("--points", type=int, default=None, help="override the workload's point count (dev only)")
+    ap.add_argument("--cpu-sample", type=int, default=160_000, help="points per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mesh", action="store_true", help="also time extract_dual_mesh(mise_iter=1) (reported separately)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import nksr_b200
+    from nksr_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = WORKLOADS[args.workload]
+    n_pts = args.points or cfg["points"]
+    W = cfg["voxel_size"]
+
+    # host (pinned) inputs: one cloud per step so that nothing can be cached across steps
+    total = args.warmup + args.steps
+    n_clouds = min(total, 2)
+    host = []
+    for s in range(n_clouds):
+        xyz, sensor = make_cloud(args.workload, 4 + s, tile=rank, points=n_pts)
+        host.append((xyz.pin_memory(), sensor.pin_memory()))
+    rec = nksr_b200.Reconstructor(dev)
+    prep = nksr_b200.get_estimate_normal_preprocess_fn(64, 85.0)
+    launches = {"n": 0}
+    orig_call = _lib.call
+
+    def counting_call(name, *a):
+        if not name.endswith("_bytes"):
+            launches["n"] += 1
+        return orig_call(name, *a)
+    _lib.call = counting_call
+    for mod in (nksr_b200.svh, nksr_b200.fields, nksr_b200.meshing, nksr_b200.reconstructor):
+        mod.call = counting_call
+
+    def step(xyz_d, sensor_d):
+        return rec.reconstruct(xyz_d, sensor=sensor_d, voxel_size=W, preprocess_fn=prep, **SOLVER)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ("value")
+    dev_inputs = [(h[0].to(dev), h[1].to(dev)) for h in host]
+    for s in range(args.warmup):
+        f = step(*dev_inputs[s % n_clouds])
+    stats = dict(rec.last_stats)
+    del f
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches["n"] = 0
+    pcg_launch = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(args.steps):
+        f = step(*dev_inputs[(args.warmup + s) % n_clouds])
+        pcg_launch += 3 * rec.last_stats.get("iterations", 0) + 1
+        del f
+    ev1.record()
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    gpu_launches = launches["n"] + pcg_launch
+    # ---- end-to-end arm: pinned host -> device -> reconstruct -> coefficients back to host
+    del dev_inputs
+    alpha_host = None
+    barrier()
+    ev0.record()
+    h2d = d2h = 0
+    for s in range(args.steps):
+        hx, hs = host[(args.warmup + s) % n_clouds]
+        xd, sd = hx.to(dev, non_blocking=True), hs.to(dev, non_blocking=True)
+        f = step(xd, sd)
+        alpha_host = f.alpha.cpu()
+        h2d = hx.numel() * 4 + hs.numel() * 4
+        d2h = alpha_host.numel() * 4
+        del f
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    # ---- roofline of the dominant kernel: SpMV inside PCG, CUDA events on the launch stream
+    rec_prof = nksr_b200.Reconstructor(dev, network=rec.network)
+    orig_init = nksr_b200.fields.KernelField.__init__
+
+    def prof_init(self, *a, **k):
+        orig_init(self, *a, **k)
+        self.solver_config["profile"] = True
+    nksr_b200.fields.KernelField.__init__ = prof_init
+    xd, sd = host[0][0].to(dev), host[0][1].to(dev)
+    fprof = rec_prof.reconstruct(xd, sensor=sd, voxel_size=W, preprocess_fn=prep, **SOLVER)
+    nksr_b200.fields.KernelField.__init__ = orig_init
+    info = fprof.solve_info
+    mesh_ms = None
+    if args.mesh:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mesh = fprof.extract_dual_mesh(mise_iter=1)
+        torch.cuda.synchronize()
+        mesh_ms = 1e3 * (time.perf_counter() - t0)
+        info = dict(info, mesh_vertices=int(mesh.v.shape[0]), mesh_faces=int(mesh.f.shape[0]))
+    n, nnz = info["n"], info["nnz"]
+    spmv_bytes = 8.0 * nnz + 12.0 * n                    # CSR fp32 values + int32 columns
+    spmv_ms = info["spmv_ms"] / max(info["spmv_launches"], 1)
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "measured"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        total_pts = n_pts * world * args.steps
+        line = {
+            "metric": "points/sec reconstruct()", "value": total_pts / (ms_dev * 1e-3), "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "points_per_gpu": n_pts, "voxel_size": W, "tree_depth": 4,
+                       "kernel_dim": 4, "feature": "sensor", "parallelism": f"chunks{world}",
+                       "l2_policy": "inputs and CSR matrix far larger than L2; alternating clouds per step",
+                       **SOLVER},
+            "e2e": {"value": total_pts / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_spmv<true> (PCG)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
+                         "launches_timed": info["spmv_launches"]},
+            "solve": {"unknowns": n, "nnz": nnz, "pcg_iterations": info["iterations"],
+                      "relative_residual": info["relative_residual"], "points_after_preprocess": stats.get("points")},
+        }
+        if mesh_ms is not None:
+            line["extract_dual_mesh_ms"] = mesh_ms
+            line["solve"].update(mesh_vertices=info["mesh_vertices"], mesh_faces=info["mesh_faces"])
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, pts, wall, out = cpu_baseline(args.workload, args.cpu_sample, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
+                                    "sample": f"{cores} spatial crops x {pts // cores} points of {args.workload} "
+                                              f"(numpy/scipy oracle, one process per core, {wall:.1f} s)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
