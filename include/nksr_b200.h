@@ -183,6 +183,19 @@ NKSR_API int nksr_mesh_triangles(const int32_t* mc_case, const int64_t* ekeys12,
 NKSR_API int nksr_layer_mask(const nksr_svh_t* svh, const float* xyz, int64_t m, int adaptive_depth,
                     float* out, void* stream);
 
+/* ---- f1: nksr.get_estimate_normal_preprocess_fn (examples/recons_waymo.py:36; CPU twin
+ *      examples/recons_waymo_cpu.py:21-41): voxel-neighbourhood PCA normals ---- */
+/* per-voxel moments (count, sum d, sum d d^T; d relative to the voxel centre) of sorted points */
+NKSR_API int nksr_voxel_moments(const int64_t* keys, int64_t n, const int32_t* range, const float* xyz,
+                       float voxel_size, float* mom10, void* stream);
+/* smallest-eigenvalue eigenvector of the covariance over the 27-neighbourhood */
+NKSR_API int nksr_voxel_pca_normals(const int32_t* nbr27, const float* mom10, int64_t n, float voxel_size,
+                           float* normal, void* stream);
+/* per point: its voxel's normal flipped to the sensor side; keep = |cos| > cos_min */
+NKSR_API int nksr_orient_normals(const float* xyz, const float* sensor, const int32_t* base,
+                        const float* vox_normal, int64_t m, float cos_min, float* normal,
+                        int32_t* keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,9 @@ _SIGNATURES = {
     "nksr_mesh_vertices": ("i", "ppqppifipp"),
     "nksr_mesh_triangles": ("i", "pppqpqpp"),
     "nksr_layer_mask": ("i", "Spqipp"),
+    "nksr_voxel_moments": ("i", "pqppfpp"),
+    "nksr_voxel_pca_normals": ("i", "ppqfpp"),
+    "nksr_orient_normals": ("i", "ppppqfppp"),
 }
 
 _lib = None
@@ -202,3 +205,27 @@ def compact_rows(rows: torch.Tensor, flags: torch.Tensor, scan: torch.Tensor, co
     if n and count:
         call("nksr_compact_rows", rows, flags, scan, n, row_bytes, out, stream_ptr(rows.device))
     return out
+
+
+class StageTimer:
+    """CUDA-event stage timer (no syncs until .report()); enabled by NKSR_STAGE_TIMES=1 or explicitly."""
+
+    def __init__(self, device, enabled=None):
+        self.enabled = bool(int(os.environ.get("NKSR_STAGE_TIMES", "0"))) if enabled is None else enabled
+        self.device, self.marks = device, []
+        self.mark("start")
+
+    def mark(self, name):
+        if self.enabled:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self.marks.append((name, ev))
+
+    def report(self):
+        if not self.enabled or len(self.marks) < 2:
+            return {}
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out

@@ -1,0 +1,153 @@
+// Normal estimation by voxel-neighbourhood PCA.
+// Replaces nksr.get_estimate_normal_preprocess_fn(knn, max_angle) (examples/recons_waymo.py:36);
+// the open CPU twin it follows is examples/recons_waymo_cpu.py:21-41 (kNN-PCA normal, flip to the
+// sensor side, drop grazing points).  Neighbourhood = the 27 voxels around the point's voxel of
+// a single-level hierarchy sized to hold ~knn points, instead of an exact kNN search.
+#include "common.cuh"
+
+namespace {
+
+// moments of the points of each voxel about the voxel centre:
+// m[0]=count, m[1..3]=sum d, m[4..9]=sum dxdx,dxdy,dxdz,dydy,dydz,dzdz
+__global__ void k_voxel_moments(const int64_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ range,
+                                const float* __restrict__ xyz, float w, float* __restrict__ mom) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ux, uy, uz;
+  morton3_decode(__ldg(keys + i), ux, uy, uz);
+  const int off = level_offset(0);
+  const float cx = ((float)(ux - off) + 0.5f) * w, cy = ((float)(uy - off) + 0.5f) * w,
+              cz = ((float)(uz - off) + 0.5f) * w;
+  float m[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) m[k] = 0.f;
+  const int rb = range[2 * i], re = range[2 * i + 1];
+  for (int q = rb; q < re; ++q) {
+    const float dx = __ldg(xyz + 3 * (int64_t)q) - cx, dy = __ldg(xyz + 3 * (int64_t)q + 1) - cy,
+                dz = __ldg(xyz + 3 * (int64_t)q + 2) - cz;
+    m[0] += 1.f; m[1] += dx; m[2] += dy; m[3] += dz;
+    m[4] += dx * dx; m[5] += dx * dy; m[6] += dx * dz; m[7] += dy * dy; m[8] += dy * dz; m[9] += dz * dz;
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) mom[i * 10 + k] = m[k];
+}
+
+__device__ __forceinline__ void jacobi_rotate(double a[3][3], double v[3][3], int p, int q) {
+  if (fabs(a[p][q]) < 1e-300) return;
+  double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+  double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+  for (int k = 0; k < 3; ++k) {
+    double akp = a[k][p], akq = a[k][q];
+    a[k][p] = c * akp - s * akq;
+    a[k][q] = s * akp + c * akq;
+  }
+  for (int k = 0; k < 3; ++k) {
+    double apk = a[p][k], aqk = a[q][k];
+    a[p][k] = c * apk - s * aqk;
+    a[q][k] = s * apk + c * aqk;
+  }
+  for (int k = 0; k < 3; ++k) {
+    double vkp = v[k][p], vkq = v[k][q];
+    v[k][p] = c * vkp - s * vkq;
+    v[k][q] = s * vkp + c * vkq;
+  }
+}
+
+// covariance of the 27-neighbourhood -> eigenvector of the smallest eigenvalue
+__global__ void k_voxel_pca(const int32_t* __restrict__ nbr27, const float* __restrict__ mom, int64_t n, float w,
+                            float* __restrict__ normal) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double cnt = 0, s[3] = {0, 0, 0}, m2[6] = {0, 0, 0, 0, 0, 0};
+  for (int sl = 0; sl < 27; ++sl) {
+    const int nb = __ldg(nbr27 + i * 27 + sl);
+    if (nb < 0) continue;
+    const float* m = mom + (int64_t)nb * 10;
+    const double c = m[0];
+    if (c == 0.0) continue;
+    int dx, dy, dz;
+    slot_to_d(sl, dx, dy, dz);
+    const double ox = dx * (double)w, oy = dy * (double)w, oz = dz * (double)w;  // neighbour centre - own centre
+    const double sx = m[1], sy = m[2], sz = m[3];
+    cnt += c;
+    s[0] += sx + c * ox; s[1] += sy + c * oy; s[2] += sz + c * oz;
+    m2[0] += m[4] + 2 * sx * ox + c * ox * ox;
+    m2[1] += m[5] + sx * oy + sy * ox + c * ox * oy;
+    m2[2] += m[6] + sx * oz + sz * ox + c * ox * oz;
+    m2[3] += m[7] + 2 * sy * oy + c * oy * oy;
+    m2[4] += m[8] + sy * oz + sz * oy + c * oy * oz;
+    m2[5] += m[9] + 2 * sz * oz + c * oz * oz;
+  }
+  float out[3] = {0.f, 0.f, 1.f};
+  if (cnt >= 3.0) {
+    const double ic = 1.0 / cnt;
+    const double mx = s[0] * ic, my = s[1] * ic, mz = s[2] * ic;
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    a[0][0] = m2[0] * ic - mx * mx; a[0][1] = a[1][0] = m2[1] * ic - mx * my; a[0][2] = a[2][0] = m2[2] * ic - mx * mz;
+    a[1][1] = m2[3] * ic - my * my; a[1][2] = a[2][1] = m2[4] * ic - my * mz; a[2][2] = m2[5] * ic - mz * mz;
+    for (int sweep = 0; sweep < 8; ++sweep) {
+      jacobi_rotate(a, v, 0, 1);
+      jacobi_rotate(a, v, 0, 2);
+      jacobi_rotate(a, v, 1, 2);
+    }
+    int k = 0;
+    if (a[1][1] < a[k][k]) k = 1;
+    if (a[2][2] < a[k][k]) k = 2;
+    double nx = v[0][k], ny = v[1][k], nz = v[2][k];
+    double nn = sqrt(nx * nx + ny * ny + nz * nz);
+    if (nn > 0) { out[0] = (float)(nx / nn); out[1] = (float)(ny / nn); out[2] = (float)(nz / nn); }
+  }
+  normal[3 * i] = out[0];
+  normal[3 * i + 1] = out[1];
+  normal[3 * i + 2] = out[2];
+}
+
+// per point: voxel normal, flipped to the sensor side; keep = |cos(view, n)| > cos_min
+__global__ void k_orient_normals(const float* __restrict__ xyz, const float* __restrict__ sensor,
+                                 const int32_t* __restrict__ base, const float* __restrict__ vox_normal, int64_t m,
+                                 float cos_min, float* __restrict__ normal, int32_t* __restrict__ keep) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int b = base[i];
+  float nx = 0.f, ny = 0.f, nz = 1.f;
+  if (b >= 0) { nx = vox_normal[3 * (int64_t)b]; ny = vox_normal[3 * (int64_t)b + 1]; nz = vox_normal[3 * (int64_t)b + 2]; }
+  float vx = sensor[3 * i] - xyz[3 * i], vy = sensor[3 * i + 1] - xyz[3 * i + 1], vz = sensor[3 * i + 2] - xyz[3 * i + 2];
+  const float vn = sqrtf(vx * vx + vy * vy + vz * vz) + 1e-6f;   // examples/recons_waymo_cpu.py:32-33
+  vx /= vn; vy /= vn; vz /= vn;
+  const float c = vx * nx + vy * ny + vz * nz;
+  if (c < 0.f) { nx = -nx; ny = -ny; nz = -nz; }
+  normal[3 * i] = nx; normal[3 * i + 1] = ny; normal[3 * i + 2] = nz;
+  keep[i] = (b >= 0 && fabsf(c) > cos_min) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nksr_voxel_moments(const int64_t* keys, int64_t n, const int32_t* range, const float* xyz, float voxel_size,
+                       float* mom, void* stream) {
+  if (n == 0) return NKSR_OK;
+  k_voxel_moments<<<grid_for(n, 128), 128, 0, as_stream(stream)>>>(keys, n, range, xyz, voxel_size, mom);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_voxel_pca_normals(const int32_t* nbr27, const float* mom, int64_t n, float voxel_size, float* normal,
+                           void* stream) {
+  if (n == 0) return NKSR_OK;
+  k_voxel_pca<<<grid_for(n, 128), 128, 0, as_stream(stream)>>>(nbr27, mom, n, voxel_size, normal);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_orient_normals(const float* xyz, const float* sensor, const int32_t* base, const float* vox_normal,
+                        int64_t m, float cos_min, float* normal, int32_t* keep, void* stream) {
+  if (m == 0) return NKSR_OK;
+  k_orient_normals<<<grid_for(m, 256), 256, 0, as_stream(stream)>>>(xyz, sensor, base, vox_normal, m, cos_min,
+                                                                     normal, keep);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+}  // extern "C"

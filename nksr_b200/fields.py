@@ -177,6 +177,8 @@ class KernelField(BaseField):
             cs.n_nrm, cs.w_nrm = 0, 0.0
         cs.w_reg = float(reg_weight)
 
+        tm = getattr(self, "_timer", None) or _lib.StageTimer(dev, enabled=False)
+        tm.mark("kernel_rows")
         cnt = torch.empty(n, dtype=torch.int32, device=dev)
         cnt_down = torch.empty(n, dtype=torch.int32, device=dev)
         call("nksr_gram_count", svh.view(), cnt, cnt_down, st)
@@ -185,12 +187,14 @@ class KernelField(BaseField):
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         call("nksr_gram_rowptr", cnt, cnt_down, n, rowptr, ws, nb, st)
         nnz = int(rowptr[-1].item())
+        tm.mark("gram_count")
         col = torch.empty(nnz, dtype=torch.int32, device=dev)
         val = torch.empty(nnz, dtype=torch.float32, device=dev)
         rhs = torch.empty(n, dtype=torch.float32, device=dev)
         diag = torch.zeros(n, dtype=torch.float32, device=dev)
         cursor = torch.zeros(n, dtype=torch.int32, device=dev)
         call("nksr_gram_fill", svh.view(), self.feat_view(), cs, cnt, rowptr, col, val, rhs, diag, cursor, st)
+        tm.mark("gram_fill")
         # deterministic storage order of the transposed (finer-level) segments
         offs = svh.offsets
         for l in range(1, svh.depth):
@@ -201,6 +205,7 @@ class KernelField(BaseField):
                 cap = max(2, 1 << (mx - 1).bit_length())
                 call("nksr_gram_sort_down", cnt, cnt_down, rowptr, offs[l], offs[l + 1], min(cap, 16384), col, val, st)
         del keep
+        tm.mark("gram_sort")
         alpha = torch.empty(n, dtype=torch.float32, device=dev)
         nb = call("nksr_pcg_workspace_bytes", n)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
@@ -208,6 +213,7 @@ class KernelField(BaseField):
         profile = int(bool(self.solver_config.get("profile")))
         call("nksr_pcg_solve", rowptr, col, val, diag, rhs, alpha, n, float(self.solver_config["tol"]),
              int(self.solver_config["max_iter"]), int(self.solver_config["check_every"]), profile, ws, nb, info, st)
+        tm.mark("pcg")
         self.alpha = alpha
         self.solve_info = {"iterations": int(info[0]), "relative_residual": float(info[1]), "n": n, "nnz": nnz}
         if profile:

@@ -75,31 +75,31 @@ def get_estimate_normal_preprocess_fn(knn: int = 64, max_angle_deg: float = 85.0
                 hi = mid
             else:
                 lo = mid
-        h = math.sqrt(lo * hi)
-        svh = SparseFeatureHierarchy(h, 1, xyz.device).build_point_splatting(xyz)
-        base = svh.locate(xyz)[0].long()
-        centre = xyz.mean(dim=0, keepdim=True)
-        xc = xyz - centre
-        mom = torch.cat([torch.ones((n, 1), device=xyz.device), xc, (xc[:, :, None] * xc[:, None, :]).reshape(n, 9)], 1)
-        acc = torch.zeros((svh.num_voxels(0), 13), device=xyz.device, dtype=torch.float64)
-        acc.index_add_(0, base, mom.double())
-        nb = svh.nbr27[0].long()
-        agg = torch.zeros_like(acc)
-        for s in range(27):
-            idx = nb[:, s]
-            agg += torch.where((idx >= 0)[:, None], acc[idx.clamp(min=0)], torch.zeros((), dtype=acc.dtype, device=acc.device))
-        cnt = agg[:, 0:1].clamp(min=1.0)
-        mean = agg[:, 1:4] / cnt
-        cov = agg[:, 4:].reshape(-1, 3, 3) / cnt[:, :, None] - mean[:, :, None] * mean[:, None, :]
-        evals, evecs = torch.linalg.eigh(cov)
-        vox_normal = evecs[:, :, 0].float()
-        nrm = vox_normal[base]
-        view = sensor - xyz
-        view = view / (torch.linalg.norm(view, dim=-1, keepdim=True) + 1e-6)
-        cos = torch.sum(view * nrm, dim=1)
-        nrm = torch.where((cos < 0)[:, None], -nrm, nrm)
-        keep = cos.abs() > math.cos(math.radians(max_angle_deg))
-        return xyz[keep], nrm[keep], None
+        h = float(torch.tensor(math.sqrt(lo * hi), dtype=torch.float32).item())
+        dev, st = xyz.device, stream_ptr(xyz.device)
+        # Morton-sort the points so that every voxel owns one contiguous range
+        hk = torch.empty(n, dtype=torch.int64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        call("nksr_point_half_keys", xyz, n, h, hk, status, st)
+        _, perm = _lib.sort_pairs(hk, torch.arange(n, dtype=torch.int32, device=dev))
+        perm = perm.long()
+        xs, ss = xyz[perm].contiguous(), sensor[perm].contiguous()
+        svh = SparseFeatureHierarchy(h, 1, dev).build_point_splatting(xs)
+        nv = svh.num_voxels(0)
+        base = svh.locate(xs)
+        ranges = torch.empty((nv, 2), dtype=torch.int32, device=dev)
+        call("nksr_row_ranges", base[0], n, ranges, nv, st)
+        mom = torch.empty((nv, 10), dtype=torch.float32, device=dev)
+        call("nksr_voxel_moments", svh.keys[0], nv, ranges, xs, h, mom, st)
+        vox_normal = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        call("nksr_voxel_pca_normals", svh.nbr27[0], mom, nv, h, vox_normal, st)
+        nrm = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        keep = torch.empty(n, dtype=torch.int32, device=dev)
+        call("nksr_orient_normals", xs, ss, base[0], vox_normal, n, math.cos(math.radians(max_angle_deg)), nrm,
+             keep, st)
+        scan = _lib.exclusive_scan32(keep)
+        cnt = int(scan[-1].item())
+        return _lib.compact_rows(xs, keep, scan, cnt), _lib.compact_rows(nrm, keep, scan, cnt), None
 
     return fn
 
@@ -169,6 +169,7 @@ class Reconstructor:
         _lib.load()
         self.chunk_tmp_device = self.device
         self.tree_depth, self.adaptive_depth = tree_depth, adaptive_depth
+        self._timer = _lib.StageTimer(self.device, enabled=False)
         self.network = (network or NKSRNetwork(dict(kernel_dim=kernel_dim, tree_depth=tree_depth,
                                                     adaptive_depth=adaptive_depth))).to(self.device)
         self.last_stats = {}
@@ -183,10 +184,14 @@ class Reconstructor:
             feat = view / (torch.linalg.norm(view, dim=-1, keepdim=True) + 1e-6)     # models/nksr_net.py:48-52
         else:
             raise ValueError("either normal or sensor (with a normal-estimating preprocess_fn) is required")
+        tm = self._timer
         svh = SparseFeatureHierarchy(voxel_size, self.tree_depth, self.device).build_point_splatting(xyz)
+        tm.mark("svh_build")
         enc = self.network.encoder(xyz, feat, svh, 0)
         feats, dec_svh, _ = self.network.unet(enc, svh, adaptive_depth=self.adaptive_depth)
         field = KernelField(dec_svh, self.network.interpolators, feats.basis_features, approx_kernel_grad)
+        field._timer = tm
+        tm.mark("network")
         field.solver_config["tol"] = float(solver_tol)
         field.solver_config["max_iter"] = int(solver_max_iter)
         ad = min(self.adaptive_depth, dec_svh.depth)
@@ -212,18 +217,22 @@ class Reconstructor:
             voxel_size = DEFAULT_VOXEL_SIZE
             return self._reconstruct_chunks(xyz, normal, sensor, voxel_size, float(chunk_size), preprocess_fn,
                                             approx_kernel_grad, solver_tol, fused_mode, solver_max_iter)
+        self._timer = _lib.StageTimer(self.device)
         if preprocess_fn is not None:
             xyz, normal, sensor = preprocess_fn(xyz, normal, sensor)
             xyz = xyz.contiguous()
+            self._timer.mark("preprocess")
         if voxel_size is None:
             voxel_size = DEFAULT_VOXEL_SIZE if detail_level is None else voxel_size_from_detail(xyz, detail_level)
         field = self._reconstruct_one(xyz, normal, sensor, float(voxel_size), approx_kernel_grad, solver_tol,
                                       fused_mode, solver_max_iter)
-        self.last_stats = dict(field.solve_info, voxel_size=float(voxel_size), points=int(xyz.shape[0]))
+        self.last_stats = dict(field.solve_info, voxel_size=float(voxel_size), points=int(xyz.shape[0]),
+                               stages_ms=self._timer.report())
         return field
 
     def _reconstruct_chunks(self, xyz, normal, sensor, voxel_size, chunk_size, preprocess_fn, approx_kernel_grad,
                             solver_tol, fused_mode, solver_max_iter, chunk_filter=None):
+        self._timer = _lib.StageTimer(self.device, enabled=False)
         margin = voxel_size * (2 ** (self.tree_depth - 1)) * 2.0       # two coarsest voxels of overlap
         cidx = torch.floor(xyz / chunk_size).long()
         cores = torch.unique(cidx, dim=0)

@@ -250,3 +250,27 @@ def test_reconstructor_end_to_end_sphere(cuda):
     m3 = f3.extract_dual_mesh()
     r3 = np.linalg.norm(_np(m3.v), axis=1)
     assert m3.f.shape[0] > 500 and abs(np.median(r3) - 3.5) < 0.05
+
+
+def test_normal_estimation_preprocess(cuda):
+    """get_estimate_normal_preprocess_fn (examples/recons_waymo.py:36; CPU twin recons_waymo_cpu.py:21-41):
+    PCA normals on a sphere point outward after the sensor-side flip; grazing points are dropped."""
+    import nksr_b200
+    xyz, nrm = clouds.sphere(60000, radius=1.0, noise=0.001)
+    sensor = (xyz * 3.0).astype(np.float32)                      # sensors outside, along the radius
+    fn = nksr_b200.get_estimate_normal_preprocess_fn(64, 85.0)
+    x2, n2, s2 = fn(torch.from_numpy(xyz).to(cuda), None, torch.from_numpy(sensor).to(cuda))
+    assert s2 is None and x2.shape == n2.shape and x2.shape[0] > 0.95 * xyz.shape[0]
+    x2, n2 = _np(x2), _np(n2)
+    radial = x2 / np.linalg.norm(x2, axis=1, keepdims=True)
+    cos = np.sum(radial * n2, axis=1)
+    assert np.median(cos) > 0.995 and (cos > 0.9).mean() > 0.98
+    assert np.allclose(np.linalg.norm(n2, axis=1), 1.0, atol=1e-4)
+    # grazing filter: a sensor in the tangent plane sees the surface edge-on
+    sensor_g = (xyz + np.cross(radial_full(xyz), np.array([0.0, 0.0, 1.0]))).astype(np.float32)
+    x3, n3, _ = fn(torch.from_numpy(xyz).to(cuda), None, torch.from_numpy(sensor_g).to(cuda))
+    assert x3.shape[0] < 0.2 * xyz.shape[0]
+
+
+def radial_full(xyz):
+    return xyz / np.linalg.norm(xyz, axis=1, keepdims=True)
