@@ -388,6 +388,7 @@ def main():
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
                          "launches_timed": info["spmv_launches"]},
+            "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
             "solve": {"unknowns": n, "nnz": nnz, "pcg_iterations": info["iterations"],
                       "relative_residual": info["relative_residual"], "points_after_preprocess": stats.get("points"),
                       "stages_ms_profiled_run": info.get("stages_ms")},
