@@ -49,6 +49,7 @@ typedef struct {
   const int32_t* parent[NKSR_MAX_DEPTH]; /* [n] index at level+1 (NULL at the top)   */
   const int32_t* child8[NKSR_MAX_DEPTH]; /* [n][8] index at level-1, -1 (NULL at 0)  */
   const int32_t* nbr27[NKSR_MAX_DEPTH];  /* [n][27] same-level neighbours, -1        */
+  const int32_t* nbr125_top;             /* [n_top][125] 5^3 neighbours of the coarsest level */
 } nksr_svh_t;
 
 /* Per-level kernel features z_i (replaces features=feat.basis_features passed to
@@ -81,6 +82,7 @@ NKSR_API int nksr_parent_index(const int64_t* keys, int64_t n, const int64_t* ke
 NKSR_API int nksr_child_table(const int64_t* keys, const int32_t* parent, int64_t n, int32_t* child8_up,
                      int64_t n_up, void* stream);
 NKSR_API int nksr_nbr27_search(const int64_t* keys, int64_t n, int32_t* nbr27, void* stream);
+NKSR_API int nksr_nbr125_search(const int64_t* keys, int64_t n, int32_t* nbr125, void* stream);
 NKSR_API int nksr_nbr27_from_parent(const int64_t* keys, const int32_t* parent, int64_t n,
                            const int32_t* nbr27_up, const int32_t* child8_up, int32_t* nbr27,
                            void* stream);
@@ -88,6 +90,10 @@ NKSR_API int nksr_nbr27_from_parent(const int64_t* keys, const int32_t* parent, 
 NKSR_API int nksr_decode_ijk(const int64_t* keys, int64_t n, int level, int32_t* ijk, void* stream);
 /* containing voxel per level for M locations: base[l*M + m], -1 if inactive */
 NKSR_API int nksr_locate(const nksr_svh_t* svh, const float* xyz, int64_t m, int32_t* base, void* stream);
+/* out[i][c] = sum of in[j][c] over the active 27-neighbourhood j of voxel i (feature pooling for
+ * the encoder stand-in that feeds models/nksr_net.py:73-78) */
+NKSR_API int nksr_pool27(const int32_t* nbr27, const float* in, int64_t n, int channels, float* out,
+                void* stream);
 /* first/last+1 sorted location of every level-l voxel: range[2*u], range[2*u+1] */
 NKSR_API int nksr_row_ranges(const int32_t* base_l, int64_t m, int32_t* range, int64_t n_l, void* stream);
 
@@ -114,6 +120,7 @@ typedef struct {
   int64_t n_nrm;
   float w_nrm;
   float w_reg;
+  int32_t nrm_compact;       /* 1: e_nrm holds compact rows [L][K][32] (nksr_build_rows mode 2) */
 } nksr_constraints_t;
 /* numeric assembly: fills col/val (CSR, int64 rowptr), rhs b, diag. cursor[n] must be zero. */
 NKSR_API int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c,
@@ -121,7 +128,7 @@ NKSR_API int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, cons
                    float* rhs, float* diag, int32_t* cursor, void* stream);
 /* sort the finer-level (transposed) segment of every row by column: deterministic storage */
 NKSR_API int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, const int64_t* rowptr,
-                        int64_t row0, int64_t row1, int cap, int32_t* col, float* val,
+                        const int32_t* rows, int64_t n_rows, int cap, int32_t* col, float* val,
                         void* stream);
 
 /* ---- a4: PCG (solver_tol, examples/recons_waymo.py:33; verbose, models/nksr_net.py:97) ---- */

@@ -22,7 +22,8 @@ class SvhT(C.Structure):
     _fields_ = [("depth", C.c_int32), ("voxel_size", C.c_float),
                 ("n", C.c_int64 * MAX_DEPTH), ("offset", C.c_int64 * MAX_DEPTH),
                 ("keys", C.c_void_p * MAX_DEPTH), ("parent", C.c_void_p * MAX_DEPTH),
-                ("child8", C.c_void_p * MAX_DEPTH), ("nbr27", C.c_void_p * MAX_DEPTH)]
+                ("child8", C.c_void_p * MAX_DEPTH), ("nbr27", C.c_void_p * MAX_DEPTH),
+                ("nbr125_top", C.c_void_p)]
 
 
 class FeatT(C.Structure):
@@ -32,7 +33,7 @@ class FeatT(C.Structure):
 class ConstraintsT(C.Structure):
     _fields_ = [("e_pos", C.c_void_p), ("range_pos", C.c_void_p), ("n_pos", C.c_int64), ("w_pos", C.c_float),
                 ("e_nrm", C.c_void_p), ("range_nrm", C.c_void_p), ("t_nrm", C.c_void_p), ("n_nrm", C.c_int64),
-                ("w_nrm", C.c_float), ("w_reg", C.c_float)]
+                ("w_nrm", C.c_float), ("w_reg", C.c_float), ("nrm_compact", C.c_int32)]
 
 
 _T = {"p": C.c_void_p, "q": C.c_int64, "i": C.c_int32, "f": C.c_float, "z": C.c_size_t,
@@ -56,12 +57,14 @@ _SIGNATURES = {
     "nksr_decode_ijk": ("i", "pqipp"),
     "nksr_locate": ("i", "Spqpp"),
     "nksr_row_ranges": ("i", "pqpqp"),
+    "nksr_pool27": ("i", "ppqipp"),
     "nksr_build_rows": ("i", "SFppqiipp"),
     "nksr_gram_count": ("i", "Sppp"),
     "nksr_scan_workspace_bytes": ("z", "q"),
     "nksr_gram_rowptr": ("i", "ppqppzp"),
     "nksr_gram_fill": ("i", "SFKppppppp" + "p"),
-    "nksr_gram_sort_down": ("i", "pppqqippp"),
+    "nksr_gram_sort_down": ("i", "ppppqippp"),
+    "nksr_nbr125_search": ("i", "pqpp"),
     "nksr_spmv": ("i", "pppppqp"),
     "nksr_pcg_workspace_bytes": ("z", "q"),
     "nksr_pcg_solve": ("i", "pppppp" + "qfiii" + "pzdp"),

@@ -11,7 +11,11 @@
 // such row r contributes  w * E[r,i] * E[r, :]  and all rows of u share the same 27-stencils on
 // level l and on every coarser level, so lane s accumulates stencil slot s in a register and
 // the warp flushes once per u into a per-warp shared-memory tile indexed by structural slot --
-// no atomics, deterministic summation order.
+// no atomics, deterministic summation order.  The round-1 ncu capture showed the kernel to be
+// instruction-issue bound in the gradient-row loop (profiles/r1_*), hence: neighbour indices
+// and row ranges are fetched lane-parallel once per row, row pointers advance by one add per
+// level, and with approx_kernel_grad the three gradient rows are rebuilt from ONE 128-byte
+// line (<phi,z_s> + tau) with nine FMAs instead of being loaded.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -21,33 +25,39 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kMaxSlots = 125 + 64 * (NKSR_MAX_DEPTH - 1);
 
+__constant__ signed char c_d27[27][3] = {
+    {-1, -1, -1}, {-1, -1, 0}, {-1, -1, 1}, {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {-1, 1, -1}, {-1, 1, 0}, {-1, 1, 1},
+    {0, -1, -1},  {0, -1, 0},  {0, -1, 1},  {0, 0, -1},  {0, 0, 0},  {0, 0, 1},  {0, 1, -1},  {0, 1, 0},  {0, 1, 1},
+    {1, -1, -1},  {1, -1, 0},  {1, -1, 1},  {1, 0, -1},  {1, 0, 0},  {1, 0, 1},  {1, 1, -1},  {1, 1, 0},  {1, 1, 1}};
+
 // same-level voxel at offset-space coords (nx,ny,nz) in the 125-neighbourhood of voxel i
-// (coords ux,uy,uz): through the parent's 27-stencil and its child table; top level: search.
+// (coords ux,uy,uz): through the parent's 27-stencil and its child table; the top level owns an
+// explicit 125-neighbour table.
 __device__ __forceinline__ int lookup_near(const nksr_svh_t& svh, int l, int i, int ux, int uy, int uz, int nx,
                                            int ny, int nz) {
   if (l + 1 < svh.depth) {
-    int p = __ldg(svh.parent[l] + i);
+    const int p = __ldg(svh.parent[l] + i);
     if (p < 0) return -1;
-    int ex = (nx >> 1) - (ux >> 1), ey = (ny >> 1) - (uy >> 1), ez = (nz >> 1) - (uz >> 1);
-    int pn = __ldg(svh.nbr27[l + 1] + (int64_t)p * 27 + (ex + 1) * 9 + (ey + 1) * 3 + (ez + 1));
+    const int ex = (nx >> 1) - (ux >> 1), ey = (ny >> 1) - (uy >> 1), ez = (nz >> 1) - (uz >> 1);
+    const int pn = __ldg(svh.nbr27[l + 1] + (int64_t)p * 27 + (ex + 1) * 9 + (ey + 1) * 3 + (ez + 1));
     if (pn < 0) return -1;
     return __ldg(svh.child8[l + 1] + (int64_t)pn * 8 + (((nx & 1) << 2) | ((ny & 1) << 1) | (nz & 1)));
   }
-  if (nx < 0 || ny < 0 || nz < 0) return -1;
-  return find_key(svh.keys[l], svh.n[l], morton3(nx, ny, nz));
+  return __ldg(svh.nbr125_top + (int64_t)i * 125 + (nx - ux + 2) * 25 + (ny - uy + 2) * 5 + (nz - uz + 2));
 }
 
 struct RowGeom {
-  int ux, uy, uz;                 // offset-space coords of the row voxel
-  int anc[NKSR_MAX_DEPTH];        // ancestor index at level l+k (anc[0] = i)
+  int ux, uy, uz;           // offset-space coords of the row voxel
+  int anc[NKSR_MAX_DEPTH];  // ancestor index at level l+k (anc[0] = i)
 };
 
 __device__ __forceinline__ void row_geom(const nksr_svh_t& svh, int l, int i, RowGeom& g) {
   morton3_decode(__ldg(svh.keys[l] + i), g.ux, g.uy, g.uz);
   g.anc[0] = i;
   int a = i;
-  for (int k = 1; l + k < svh.depth; ++k) {
-    a = a >= 0 ? __ldg(svh.parent[l + k - 1] + a) : -1;
+#pragma unroll
+  for (int k = 1; k < NKSR_MAX_DEPTH; ++k) {
+    if (l + k < svh.depth) a = a >= 0 ? __ldg(svh.parent[l + k - 1] + a) : -1;
     g.anc[k] = a;
   }
 }
@@ -57,17 +67,20 @@ __device__ __forceinline__ void row_geom(const nksr_svh_t& svh, int l, int i, Ro
 __device__ __forceinline__ int slot_column(const nksr_svh_t& svh, int l, const RowGeom& g, int t, int& k_out) {
   if (t < 125) {
     k_out = 0;
-    int dx = t / 25 - 2, dy = (t / 5) % 5 - 2, dz = t % 5 - 2;
+    const int dx = t / 25 - 2, dy = (t / 5) % 5 - 2, dz = t % 5 - 2;
     return lookup_near(svh, l, g.anc[0], g.ux, g.uy, g.uz, g.ux + dx, g.uy + dy, g.uz + dz);
   }
   int q = t - 125;
-  int k = 1 + (q >> 6);
+  const int k = 1 + (q >> 6);
   k_out = k;
   q &= 63;
-  int ox = q >> 4, oy = (q >> 2) & 3, oz = q & 3;
-  int cx = (((g.ux - 1) >> k) - 1) + ox, cy = (((g.uy - 1) >> k) - 1) + oy, cz = (((g.uz - 1) >> k) - 1) + oz;
+  const int ox = q >> 4, oy = (q >> 2) & 3, oz = q & 3;
+  const int cx = (((g.ux - 1) >> k) - 1) + ox, cy = (((g.uy - 1) >> k) - 1) + oy, cz = (((g.uz - 1) >> k) - 1) + oz;
   if (cx > ((g.ux + 1) >> k) + 1 || cy > ((g.uy + 1) >> k) + 1 || cz > ((g.uz + 1) >> k) + 1) return -1;
-  int a = g.anc[k];
+  int a = g.anc[0];
+#pragma unroll
+  for (int j = 1; j < NKSR_MAX_DEPTH; ++j)
+    if (j == k) a = g.anc[j];
   if (a < 0) return -1;
   return lookup_near(svh, l + k, a, g.ux >> k, g.uy >> k, g.uz >> k, cx, cy, cz);
 }
@@ -108,6 +121,7 @@ __global__ void k_set_last(const int32_t* cnt, const int32_t* cnt_down, int64_t 
   if (threadIdx.x == 0 && blockIdx.x == 0) rowptr[n] = rowptr[n - 1] + cnt[n - 1] + cnt_down[n - 1];
 }
 
+template <bool COMPACT, int MAXL>
 __global__ void __launch_bounds__(kWarps * 32)
 k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_total,
             const int32_t* __restrict__ cnt, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col_out,
@@ -125,61 +139,105 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
   const int nslots = 125 + 64 * nup;
   float* acc = smem + wid * kMaxSlots;
   for (int t = lane; t < nslots; t += 32) acc[t] = 0.f;
-  __syncwarp();
   RowGeom g;
   row_geom(svh, l, i, g);
   const int64_t N = cs.n_pos, K = cs.n_nrm;
-  // per-level base offsets of the range tables (levels concatenated)
-  int64_t roff = 0;
-  for (int q = 0; q < l; ++q) roff += svh.n[q];
-  const int32_t* rp = cs.range_pos ? cs.range_pos + 2 * roff : nullptr;
-  const int32_t* rn = cs.range_nrm ? cs.range_nrm + 2 * roff : nullptr;
+  const int32_t* rp = cs.range_pos ? cs.range_pos + 2 * svh.offset[l] : nullptr;
+  const int32_t* rn = cs.range_nrm ? cs.range_nrm + 2 * svh.offset[l] : nullptr;
   float bsum = 0.f;
-  int ldx, ldy, ldz;
-  slot_to_d(lane < 27 ? lane : 13, ldx, ldy, ldz);
+  const int sl = lane < 27 ? lane : 13;
+  const int ldx = c_d27[sl][0], ldy = c_d27[sl][1], ldz = c_d27[sl][2];
+  // lane-parallel prefetch of the 27 neighbour voxels and their constraint-row ranges
+  const int my_u = lane < 27 ? __ldg(svh.nbr27[l] + (int64_t)i * 27 + lane) : -1;
+  int my_pb = 0, my_pe = 0, my_nb = 0, my_ne = 0;
+  if (my_u >= 0) {
+    if (rp) { my_pb = __ldg(rp + 2 * (int64_t)my_u); my_pe = __ldg(rp + 2 * (int64_t)my_u + 1); }
+    if (rn) { my_nb = __ldg(rn + 2 * (int64_t)my_u); my_ne = __ldg(rn + 2 * (int64_t)my_u + 1); }
+  }
+  // quadratic B-spline as polynomials in tau for this lane's offset d (SPEC S4):
+  // b = c0 + tau (c1 + c2 tau), db = c1 + 2 c2 tau
+  const float cx0 = ldx == 0 ? 0.75f : 0.125f, cx1 = 0.5f * (float)ldx, cx2 = ldx == 0 ? -1.f : 0.5f;
+  const float cy0 = ldy == 0 ? 0.75f : 0.125f, cy1 = 0.5f * (float)ldy, cy2 = ldy == 0 ? -1.f : 0.5f;
+  const float cz0 = ldz == 0 ? 0.75f : 0.125f, cz1 = 0.5f * (float)ldz, cz2 = ldz == 0 ? -1.f : 0.5f;
+  const float inv_wl = 1.f / (svh.voxel_size * (float)(1 << l));
+  const int64_t pos_level = N * NKSR_ROW_STRIDE;
+  const int64_t nrm_level = K * NKSR_ROW_STRIDE * (COMPACT ? 1 : 3);
+  __syncwarp();
 
   for (int us = 0; us < 27; ++us) {
-    const int u = __ldg(svh.nbr27[l] + (int64_t)i * 27 + us);
+    const int u = __shfl_sync(0xffffffffu, my_u, us);
     if (u < 0) continue;
+    const int pb = __shfl_sync(0xffffffffu, my_pb, us), pe = __shfl_sync(0xffffffffu, my_pe, us);
+    const int nb = __shfl_sync(0xffffffffu, my_nb, us), ne = __shfl_sync(0xffffffffu, my_ne, us);
+    if (pb == pe && nb == ne) continue;
     const int si = 26 - us;  // slot of i inside u's stencil
-    float r[NKSR_MAX_DEPTH];
+    float r[MAXL];
 #pragma unroll
-    for (int k = 0; k < NKSR_MAX_DEPTH; ++k) r[k] = 0.f;
-    if (rp) {
-      const int rb = __ldg(rp + 2 * (int64_t)u), re = __ldg(rp + 2 * (int64_t)u + 1);
-      for (int q = rb; q < re; ++q) {
-        const float a = cs.w_pos * __ldg(cs.e_pos + ((int64_t)l * N + q) * NKSR_ROW_STRIDE + si);
+    for (int k = 0; k < MAXL; ++k) r[k] = 0.f;
+    for (int q = pb; q < pe; ++q) {
+      const float* p0 = cs.e_pos + ((int64_t)l * N + q) * NKSR_ROW_STRIDE;
+      const float a = cs.w_pos * __ldg(p0 + si);
+      const float* pk = p0 + lane;
 #pragma unroll
-        for (int k = 0; k < NKSR_MAX_DEPTH; ++k)
-          if (k <= nup) r[k] = fmaf(a, __ldg(cs.e_pos + ((int64_t)(l + k) * N + q) * NKSR_ROW_STRIDE + lane), r[k]);
-      }
+      for (int k = 0; k < MAXL; ++k)
+        if (k <= nup) { r[k] = fmaf(a, __ldg(pk), r[k]); pk += pos_level; }
     }
-    if (rn) {
-      const int rb = __ldg(rn + 2 * (int64_t)u), re = __ldg(rn + 2 * (int64_t)u + 1);
-      for (int q = rb; q < re; ++q) {
+    if (COMPACT) {
+      // one line per (location, level): <phi,z_s> in slots 0..26, tau in 27..29;
+      // E_a[s] = dB_a B_b B_c <phi,z_s> / W_level
+      for (int q = nb; q < ne; ++q) {
+        const float* pk = cs.e_nrm + ((int64_t)l * K + q) * NKSR_ROW_STRIDE + lane;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, iw = inv_wl;
+#pragma unroll
+        for (int k = 0; k < MAXL; ++k) {
+          if (k <= nup) {
+            const float line = __ldg(pk);
+            pk += nrm_level;
+            const float tx = __shfl_sync(0xffffffffu, line, 27), ty = __shfl_sync(0xffffffffu, line, 28),
+                        tz = __shfl_sync(0xffffffffu, line, 29);
+            const float bx = fmaf(fmaf(cx2, tx, cx1), tx, cx0), dbx = fmaf(2.f * cx2, tx, cx1);
+            const float by = fmaf(fmaf(cy2, ty, cy1), ty, cy0), dby = fmaf(2.f * cy2, ty, cy1);
+            const float bz = fmaf(fmaf(cz2, tz, cz1), tz, cz0), dbz = fmaf(2.f * cz2, tz, cz1);
+            const float sc = (lane < 27 ? line : 0.f) * iw;
+            const float e0 = dbx * by * bz * sc, e1 = bx * dby * bz * sc, e2 = bx * by * dbz * sc;
+            if (k == 0) {
+              a0 = cs.w_nrm * __shfl_sync(0xffffffffu, e0, si);
+              a1 = cs.w_nrm * __shfl_sync(0xffffffffu, e1, si);
+              a2 = cs.w_nrm * __shfl_sync(0xffffffffu, e2, si);
+              const float* t = cs.t_nrm + (int64_t)q * 3;
+              bsum = fmaf(a0, __ldg(t), fmaf(a1, __ldg(t + 1), fmaf(a2, __ldg(t + 2), bsum)));
+            }
+            r[k] = fmaf(a0, e0, fmaf(a1, e1, fmaf(a2, e2, r[k])));
+            iw *= 0.5f;
+          }
+        }
+      }
+    } else {
+      for (int q = nb; q < ne; ++q) {
+        const float* p0 = cs.e_nrm + ((int64_t)l * K + q) * (3 * NKSR_ROW_STRIDE);
+        const float* t = cs.t_nrm + (int64_t)q * 3;
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) {
-          const float a = cs.w_nrm * __ldg(cs.e_nrm + (((int64_t)l * K + q) * 3 + ax) * NKSR_ROW_STRIDE + si);
-          bsum = fmaf(a, __ldg(cs.t_nrm + (int64_t)q * 3 + ax), bsum);
+          const float a = cs.w_nrm * __ldg(p0 + ax * NKSR_ROW_STRIDE + si);
+          bsum = fmaf(a, __ldg(t + ax), bsum);
+          const float* pk = p0 + ax * NKSR_ROW_STRIDE + lane;
 #pragma unroll
-          for (int k = 0; k < NKSR_MAX_DEPTH; ++k)
-            if (k <= nup)
-              r[k] = fmaf(a, __ldg(cs.e_nrm + (((int64_t)(l + k) * K + q) * 3 + ax) * NKSR_ROW_STRIDE + lane), r[k]);
+          for (int k = 0; k < MAXL; ++k)
+            if (k <= nup) { r[k] = fmaf(a, __ldg(pk), r[k]); pk += nrm_level; }
         }
       }
     }
     // flush: every lane < 27 owns a distinct structural slot per level
     if (lane < 27) {
-      int udx, udy, udz;
-      slot_to_d(us, udx, udy, udz);
+      const int udx = c_d27[us][0], udy = c_d27[us][1], udz = c_d27[us][2];
       acc[(udx + ldx + 2) * 25 + (udy + ldy + 2) * 5 + (udz + ldz + 2)] += r[0];
       const int vx = g.ux + udx, vy = g.uy + udy, vz = g.uz + udz;  // coords of u
 #pragma unroll
-      for (int k = 1; k < NKSR_MAX_DEPTH; ++k) {
+      for (int k = 1; k < MAXL; ++k) {
         if (k <= nup) {
-          int ox = ((vx >> k) + ldx) - (((g.ux - 1) >> k) - 1);
-          int oy = ((vy >> k) + ldy) - (((g.uy - 1) >> k) - 1);
-          int oz = ((vz >> k) + ldz) - (((g.uz - 1) >> k) - 1);
+          const int ox = ((vx >> k) + ldx) - (((g.ux - 1) >> k) - 1);
+          const int oy = ((vy >> k) + ldy) - (((g.uy - 1) >> k) - 1);
+          const int oz = ((vz >> k) + ldz) - (((g.uz - 1) >> k) - 1);
           acc[125 + 64 * (k - 1) + (ox << 4) + (oy << 2) + oz] += r[k];
         }
       }
@@ -187,17 +245,14 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
     __syncwarp();
   }
   // regulariser: R_{i,i+d} = w_reg * B3(d) * <z_i, z_{i+d}>  (SPEC S5)
-  if (cs.w_reg != 0.f && lane < 27) {
-    const int nb = __ldg(svh.nbr27[l] + (int64_t)i * 27 + lane);
-    if (nb >= 0) {
-      const int C = feat.channels;
-      const float* zi = feat.z[l] + (int64_t)i * C;
-      const float* zn = feat.z[l] + (int64_t)nb * C;
-      float d = 0.f;
-      for (int c = 0; c < C; ++c) d = fmaf(__ldg(zi + c), __ldg(zn + c), d);
-      const float bw = (ldx == 0 ? 0.75f : 0.125f) * (ldy == 0 ? 0.75f : 0.125f) * (ldz == 0 ? 0.75f : 0.125f);
-      acc[(ldx + 2) * 25 + (ldy + 2) * 5 + (ldz + 2)] += cs.w_reg * bw * d;
-    }
+  if (cs.w_reg != 0.f && my_u >= 0) {
+    const int C = feat.channels;
+    const float* zi = feat.z[l] + (int64_t)i * C;
+    const float* zn = feat.z[l] + (int64_t)my_u * C;
+    float d = 0.f;
+    for (int c = 0; c < C; ++c) d = fmaf(__ldg(zi + c), __ldg(zn + c), d);
+    const float bw = (ldx == 0 ? 0.75f : 0.125f) * (ldy == 0 ? 0.75f : 0.125f) * (ldz == 0 ? 0.75f : 0.125f);
+    acc[(ldx + 2) * 25 + (ldy + 2) * 5 + (ldz + 2)] += cs.w_reg * bw * d;
   }
   __syncwarp();
   // write-out in structural order
@@ -226,15 +281,15 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
   if (lane == 0) rhs[row] = bsum;
 }
 
-// bitonic sort of each row's finer-level segment by column (block per row)
+// bitonic sort of the finer-level segment of each listed row by column (block per row)
 __global__ void k_sort_down(const int32_t* __restrict__ cnt, const int32_t* __restrict__ cnt_down,
-                            const int64_t* __restrict__ rowptr, int64_t row0, int64_t n, int32_t* __restrict__ col,
-                            float* __restrict__ val, int cap) {
+                            const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rows, int64_t n_rows,
+                            int32_t* __restrict__ col, float* __restrict__ val, int cap) {
   extern __shared__ unsigned char raw[];
   int32_t* sc = reinterpret_cast<int32_t*>(raw);
   float* sv = reinterpret_cast<float*>(raw) + cap;
-  const int64_t row = row0 + blockIdx.x;
-  if (row >= n) return;
+  if (blockIdx.x >= n_rows) return;
+  const int64_t row = rows[blockIdx.x];
   const int m = cnt_down[row];
   if (m <= 1 || m > cap) return;
   const int64_t p0 = rowptr[row] + cnt[row];
@@ -248,13 +303,13 @@ __global__ void k_sort_down(const int32_t* __restrict__ cnt, const int32_t* __re
   for (int k = 2; k <= m2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = threadIdx.x; t < m2; t += blockDim.x) {
-        int p = t ^ j;
+        const int p = t ^ j;
         if (p > t) {
-          bool up = (t & k) == 0;
-          int a = sc[t], b = sc[p];
+          const bool up = (t & k) == 0;
+          const int a = sc[t], b = sc[p];
           if ((a > b) == up) {
             sc[t] = b; sc[p] = a;
-            float x = sv[t]; sv[t] = sv[p]; sv[p] = x;
+            const float x = sv[t]; sv[t] = sv[p]; sv[p] = x;
           }
         }
       }
@@ -276,7 +331,7 @@ static int64_t total_unknowns(const nksr_svh_t* svh) {
 extern "C" {
 
 int nksr_gram_count(const nksr_svh_t* svh, int32_t* cnt, int32_t* cnt_down, void* stream) {
-  if (!svh || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
+  if (!svh || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH || !svh->nbr125_top) return NKSR_E_INVALID;
   const int64_t n = total_unknowns(svh);
   if (n == 0) return NKSR_OK;
   if (cudaMemsetAsync(cnt_down, 0, (size_t)n * sizeof(int32_t), as_stream(stream)) != cudaSuccess) return NKSR_E_CUDA;
@@ -312,27 +367,37 @@ int nksr_gram_rowptr(const int32_t* cnt, const int32_t* cnt_down, int64_t n, int
 int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c, const int32_t* cnt,
                    const int64_t* rowptr, int32_t* col, float* val, float* rhs, float* diag, int32_t* cursor,
                    void* stream) {
-  if (!svh || !feat || !c || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
+  if (!svh || !feat || !c || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH || !svh->nbr125_top)
+    return NKSR_E_INVALID;
   const int64_t n = total_unknowns(svh);
   if (n == 0) return NKSR_OK;
   const size_t smem = (size_t)kWarps * kMaxSlots * sizeof(float);
-  k_gram_fill<<<grid_for(n, kWarps), kWarps * 32, smem, as_stream(stream)>>>(*svh, *feat, *c, n, cnt, rowptr, col,
-                                                                             val, rhs, diag, cursor);
+  const int grid = grid_for(n, kWarps);
+  cudaStream_t s = as_stream(stream);
+#define NKSR_FILL(COMPACT, MAXL) \
+  k_gram_fill<COMPACT, MAXL><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, val, rhs, diag, cursor)
+  if (svh->depth <= 4) {
+    if (c->nrm_compact) NKSR_FILL(true, 4); else NKSR_FILL(false, 4);
+  } else {
+    if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH); else NKSR_FILL(false, NKSR_MAX_DEPTH);
+  }
+#undef NKSR_FILL
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }
 
-int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, const int64_t* rowptr, int64_t row0,
-                        int64_t row1, int cap, int32_t* col, float* val, void* stream) {
-  // one block per row in [row0,row1); segments longer than `cap` (a power of two <= 16384) are
-  // left in insertion order.
-  if (row1 <= row0) return NKSR_OK;
+int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, const int64_t* rowptr, const int32_t* rows,
+                        int64_t n_rows, int cap, int32_t* col, float* val, void* stream) {
+  // one block per listed row; segments longer than `cap` (a power of two <= 16384) are left in
+  // insertion order.
+  if (n_rows <= 0) return NKSR_OK;
   if (cap < 2 || cap > 16384 || (cap & (cap - 1))) return NKSR_E_INVALID;
   if (cap * 8 > 48 * 1024 &&
       cudaFuncSetAttribute(k_sort_down, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8) != cudaSuccess)
     return NKSR_E_CUDA;
-  k_sort_down<<<(unsigned)(row1 - row0), cap >= 1024 ? 256 : 64, cap * 8, as_stream(stream)>>>(
-      cnt, cnt_down, rowptr, row0, row1, col, val, cap);
+  const int threads = cap >= 2048 ? 256 : (cap >= 256 ? 128 : 32);
+  k_sort_down<<<(unsigned)n_rows, threads, cap * 8, as_stream(stream)>>>(cnt, cnt_down, rowptr, rows, n_rows, col,
+                                                                         val, cap);
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

@@ -7,8 +7,11 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
-// one warp per (location, level): writes a 128-byte value row or three gradient rows
-template <bool GRAD>
+// one warp per (location, level): writes a 128-byte value row (MODE 0), three gradient rows
+// (MODE 1) or one compact gradient row (MODE 2, approx_kernel_grad only): slots 0..26 hold
+// <phi(x), z_s>, slots 27..29 the local coordinate tau -- the three gradient rows
+// dB_a B_b B_c <phi,z_s> / W_l are rebuilt from it inside the assembly kernel.
+template <int MODE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, const int32_t* __restrict__ base,
              int64_t m, bool fullgrad, float* __restrict__ e) {
@@ -19,6 +22,7 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
   const int l = (int)(warp / m);
   const int64_t i = warp - (int64_t)l * m;
   const int b = __ldg(base + (int64_t)l * m + i);
+  constexpr bool GRAD = MODE == 1;
   float* out = e + (GRAD ? ((int64_t)l * m + i) * 3 * NKSR_ROW_STRIDE : ((int64_t)l * m + i) * NKSR_ROW_STRIDE);
   if (b < 0) {
     out[lane] = 0.f;
@@ -33,6 +37,8 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
     out[lane] = r.dk[0];
     out[32 + lane] = r.dk[1];
     out[64 + lane] = r.dk[2];
+  } else if (MODE == 2) {
+    out[lane] = lane < 27 ? r.dot : (lane < 30 ? r.tau[lane - 27] : 0.f);
   } else {
     out[lane] = r.k;
   }
@@ -130,10 +136,14 @@ int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float*
   int64_t warps = m * svh->depth;
   int grid = grid_for(warps, kWarpsPerBlock);
   if (mode == 0)
-    k_build_rows<false><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m, false, e);
+    k_build_rows<0><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m, false, e);
+  else if (mode == 1)
+    k_build_rows<1><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m,
+                                                                          !approx_kernel_grad, e);
+  else if (mode == 2 && approx_kernel_grad)
+    k_build_rows<2><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m, false, e);
   else
-    k_build_rows<true><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m,
-                                                                             !approx_kernel_grad, e);
+    return NKSR_E_INVALID;
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

@@ -8,6 +8,8 @@ struct LaneKernel {
   int nb;       // neighbour voxel index of this lane's slot (-1: none / lane >= 27)
   float k;      // K_l(x, nb)
   float dk[3];  // grad_x K_l(x, nb)
+  float dot;    // <phi_l(x), z_nb>  (0 when nb < 0)
+  float tau[3]; // local coordinate of x in the containing voxel
 };
 
 // weights of neighbour d in {-1,0,1} along one axis at local coordinate tau in [-.5,.5)
@@ -86,6 +88,8 @@ __device__ __forceinline__ LaneKernel eval_level_lane(const int64_t* __restrict_
     }
   }
   r.k = ok ? B3 * dot : 0.f;
+  r.dot = ok ? dot : 0.f;
+  r.tau[0] = tx; r.tau[1] = ty; r.tau[2] = tz;
   if (GRAD) {
     const float iw = 1.f / wl;
     r.dk[0] = ok ? (dbx * by * bz * dot + B3 * ddot[0]) * iw : 0.f;

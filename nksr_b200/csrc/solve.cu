@@ -26,16 +26,22 @@ k_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
   double local = 0.0;
   for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + wid; row < n; row += nwarps) {
     const int64_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-    float s0 = 0.f, s1 = 0.f;
+    // matrix stream: evict-first loads (read once per SpMV); x: read-only path, stays in L1/L2.
+    // Four independent 128 B column + value requests per lane keep ~1 KB per warp in flight.
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int64_t p = b + lane;
-    for (; p + 32 < e; p += 64) {
-      const int c0 = __ldg(col + p), c1 = __ldg(col + p + 32);
-      const float v0 = __ldg(val + p), v1 = __ldg(val + p + 32);
+    for (; p < e; p += 128) {   // predicated tail: absent entries read as (col 0, value 0)
+      const bool q1 = p + 32 < e, q2 = p + 64 < e, q3 = p + 96 < e;
+      const int c0 = __ldcs(col + p), c1 = q1 ? __ldcs(col + p + 32) : 0, c2 = q2 ? __ldcs(col + p + 64) : 0,
+                c3 = q3 ? __ldcs(col + p + 96) : 0;
+      const float v0 = __ldcs(val + p), v1 = q1 ? __ldcs(val + p + 32) : 0.f, v2 = q2 ? __ldcs(val + p + 64) : 0.f,
+                  v3 = q3 ? __ldcs(val + p + 96) : 0.f;
       s0 = fmaf(v0, __ldg(x + c0), s0);
       s1 = fmaf(v1, __ldg(x + c1), s1);
+      s2 = fmaf(v2, __ldg(x + c2), s2);
+      s3 = fmaf(v3, __ldg(x + c3), s3);
     }
-    if (p < e) s0 = fmaf(__ldg(val + p), __ldg(x + __ldg(col + p)), s0);
-    float s = warp_sum(s0 + s1);
+    float s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) {
       y[row] = s;
       if (DOT) local += (double)s * (double)__ldg(x + row);

@@ -78,6 +78,20 @@ __global__ void k_nbr27_search(const int64_t* __restrict__ keys, int64_t n, int3
   nbr[t] = r;
 }
 
+__global__ void k_nbr125_search(const int64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ nbr) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n * 125) return;
+  int64_t i = t / 125;
+  int s = (int)(t - i * 125);
+  int ux, uy, uz;
+  morton3_decode(__ldg(keys + i), ux, uy, uz);
+  ux += s / 25 - 2; uy += (s / 5) % 5 - 2; uz += s % 5 - 2;
+  int r = -1;
+  if (ux >= 0 && uy >= 0 && uz >= 0 && ux < NKSR_KEY_LIMIT && uy < NKSR_KEY_LIMIT && uz < NKSR_KEY_LIMIT)
+    r = find_key(keys, n, morton3(ux, uy, uz));
+  nbr[t] = r;
+}
+
 __global__ void k_nbr27_from_parent(const int64_t* __restrict__ keys, const int32_t* __restrict__ parent, int64_t n,
                                     const int32_t* __restrict__ nbr_up, const int32_t* __restrict__ child8_up,
                                     int32_t* __restrict__ nbr) {
@@ -134,6 +148,20 @@ __global__ void k_locate(nksr_svh_t svh, const float* __restrict__ xyz, int64_t 
       idx = __ldg(svh.child8[l + 1] + (int64_t)idx * 8 + slot);
     }
     base[(int64_t)l * m + i] = idx;
+  }
+}
+
+// out[i][c] = sum over the active 27-neighbourhood of in[nb][c]; one warp per voxel, lane = slot
+__global__ void k_pool27(const int32_t* __restrict__ nbr27, const float* __restrict__ in, int64_t n, int channels,
+                         float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int nb = lane < 27 ? __ldg(nbr27 + i * 27 + lane) : -1;
+  for (int c = 0; c < channels; ++c) {
+    float v = nb >= 0 ? __ldg(in + (int64_t)nb * channels + c) : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) out[i * channels + c] = v;
   }
 }
 
@@ -262,6 +290,13 @@ int nksr_nbr27_search(const int64_t* keys, int64_t n, int32_t* nbr27, void* stre
   return NKSR_OK;
 }
 
+int nksr_nbr125_search(const int64_t* keys, int64_t n, int32_t* nbr125, void* stream) {
+  if (n == 0) return NKSR_OK;
+  k_nbr125_search<<<grid_for(n * 125, 256), 256, 0, as_stream(stream)>>>(keys, n, nbr125);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
 int nksr_nbr27_from_parent(const int64_t* keys, const int32_t* parent, int64_t n, const int32_t* nbr27_up,
                            const int32_t* child8_up, int32_t* nbr27, void* stream) {
   if (n == 0) return NKSR_OK;
@@ -283,6 +318,14 @@ int nksr_locate(const nksr_svh_t* svh, const float* xyz, int64_t m, int32_t* bas
   if (!svh || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
   if (m == 0) return NKSR_OK;
   k_locate<<<grid_for(m, 256), 256, 0, as_stream(stream)>>>(*svh, xyz, m, svh->voxel_size * 0.5f, base);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_pool27(const int32_t* nbr27, const float* in, int64_t n, int channels, float* out, void* stream) {
+  if (channels < 1) return NKSR_E_INVALID;
+  if (n == 0) return NKSR_OK;
+  k_pool27<<<grid_for(n, 8), 256, 0, as_stream(stream)>>>(nbr27, in, n, channels, out);
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

@@ -141,7 +141,7 @@ class KernelField(BaseField):
         offs = svh.offsets
         for l in range(svh.depth):
             call("nksr_row_ranges", base[l], m, ranges[offs[l]:], svh.num_voxels(l), st)
-        width = _lib.ROW_STRIDE * (3 if mode else 1)
+        width = _lib.ROW_STRIDE * (3 if mode == 1 else 1)
         e = torch.empty((svh.depth, m, width), dtype=torch.float32, device=dev)
         call("nksr_build_rows", svh.view(), self.feat_view(), xs, base, m, mode,
              int(self.approx_kernel_grad), e, st)
@@ -168,7 +168,10 @@ class KernelField(BaseField):
         if normal_xyz is not None and normal_xyz.shape[0] > 0:
             normal_xyz = normal_xyz.detach().to(dev, torch.float32).contiguous()
             normal_value = normal_value.detach().to(dev, torch.float32).contiguous()
-            _, t_nrm, _, range_nrm, e_nrm = self._sorted_rows(normal_xyz, 1, normal_value)
+            # approx_kernel_grad: compact gradient rows (one 128 B line per location and level)
+            nrm_mode = 2 if self.approx_kernel_grad else 1
+            _, t_nrm, _, range_nrm, e_nrm = self._sorted_rows(normal_xyz, nrm_mode, normal_value)
+            cs.nrm_compact = int(nrm_mode == 2)
             keep += [t_nrm, range_nrm, e_nrm]
             cs.e_nrm, cs.range_nrm, cs.t_nrm = e_nrm.data_ptr(), range_nrm.data_ptr(), t_nrm.data_ptr()
             cs.n_nrm, cs.w_nrm = normal_xyz.shape[0], float(normal_weight)
@@ -196,14 +199,16 @@ class KernelField(BaseField):
         call("nksr_gram_fill", svh.view(), self.feat_view(), cs, cnt, rowptr, col, val, rhs, diag, cursor, st)
         tm.mark("gram_fill")
         # deterministic storage order of the transposed (finer-level) segments
+        # (rows binned by segment length so that short rows do not pay for a large tile)
         offs = svh.offsets
-        for l in range(1, svh.depth):
-            if svh.num_voxels(l) == 0:
-                continue
-            mx = int(cnt_down[offs[l]:offs[l + 1]].max().item())
-            if mx > 1:
-                cap = max(2, 1 << (mx - 1).bit_length())
-                call("nksr_gram_sort_down", cnt, cnt_down, rowptr, offs[l], offs[l + 1], min(cap, 16384), col, val, st)
+        if svh.depth > 1 and n > offs[1]:
+            seg = cnt_down[offs[1]:]
+            lo_b = 1
+            for cap in (32, 128, 512, 2048, 16384):
+                rows = (torch.nonzero((seg > lo_b) & (seg <= cap)).reshape(-1) + offs[1]).to(torch.int32)
+                lo_b = cap
+                if rows.numel():
+                    call("nksr_gram_sort_down", cnt, cnt_down, rowptr, rows, rows.numel(), cap, col, val, st)
         del keep
         tm.mark("gram_sort")
         alpha = torch.empty(n, dtype=torch.float32, device=dev)

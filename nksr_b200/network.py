@@ -88,19 +88,25 @@ class NKSRNetwork(nn.Module):
     # ---- encoder: pool point features into the voxels of every level ---------------------
     @torch.no_grad()
     def encoder(self, xyz: torch.Tensor, feat, svh: SparseFeatureHierarchy, depth: int = 0):
-        base = svh.locate(xyz).long()                                   # (L, N)
-        pooled = []
+        from ._lib import call, stream_ptr
+        base0 = svh.locate(xyz)[0].long()                               # finest containing voxel
         ones = torch.ones((xyz.shape[0], 1), device=xyz.device)
         src = torch.cat([feat.to(torch.float32) if feat is not None else torch.zeros_like(xyz), ones], dim=1)
+        pooled, acc = [], None
         for l in range(svh.depth):
             n = svh.num_voxels(l)
-            acc = torch.zeros((n, 4), device=xyz.device)
-            ok = base[l] >= 0
-            acc.index_add_(0, base[l][ok], src[ok])
+            if l == 0:
+                acc = torch.zeros((n, 4), device=xyz.device)
+                ok = base0 >= 0
+                acc.index_add_(0, base0[ok], src[ok])
+            else:                                                       # sum of the (<= 8) children
+                ch = svh.child8[l].long()
+                acc = torch.where((ch >= 0)[:, :, None], acc[ch.clamp(min=0)],
+                                  torch.zeros((), device=xyz.device)).sum(dim=1).contiguous()
             # smooth over the 27-neighbourhood so that splat-only voxels receive a value
-            nb = svh.nbr27[l].long()
-            gathered = torch.where((nb >= 0)[:, :, None], acc[nb.clamp(min=0)], torch.zeros((), device=xyz.device))
-            pooled.append(gathered.sum(dim=1))
+            out = torch.empty_like(acc)
+            call("nksr_pool27", svh.nbr27[l], acc, n, 4, out, stream_ptr(xyz.device))
+            pooled.append(out)
         return SimpleNamespace(svh=svh, pooled=pooled)
 
     # ---- "U-Net": heads on the pooled statistics; hierarchy passes through -----------------

@@ -56,6 +56,7 @@ class SparseFeatureHierarchy:
         self.parent: List[Optional[torch.Tensor]] = [None] * depth
         self.child8: List[Optional[torch.Tensor]] = [None] * depth
         self.nbr27: List[Optional[torch.Tensor]] = [None] * depth
+        self.nbr125_top: Optional[torch.Tensor] = None
         self._view = None
 
     # ------------------------------------------------------------------ construction
@@ -96,6 +97,8 @@ class SparseFeatureHierarchy:
         top = self.keys[L - 1]
         self.nbr27[L - 1] = torch.empty((top.numel(), 27), dtype=torch.int32, device=dev)
         call("nksr_nbr27_search", top, top.numel(), self.nbr27[L - 1], st)
+        self.nbr125_top = torch.empty((top.numel(), 125), dtype=torch.int32, device=dev)
+        call("nksr_nbr125_search", top, top.numel(), self.nbr125_top, st)
         for l in range(L - 2, -1, -1):
             n = self.keys[l].numel()
             self.nbr27[l] = torch.empty((n, 27), dtype=torch.int32, device=dev)
@@ -144,6 +147,7 @@ class SparseFeatureHierarchy:
                 v.parent[l] = self.parent[l].data_ptr() if self.parent[l] is not None else None
                 v.child8[l] = self.child8[l].data_ptr() if self.child8[l] is not None else None
                 v.nbr27[l] = self.nbr27[l].data_ptr() if self.nbr27[l] is not None else None
+            v.nbr125_top = self.nbr125_top.data_ptr() if self.nbr125_top is not None else None
             self._view = v
         return self._view
 
@@ -181,5 +185,7 @@ class SparseFeatureHierarchy:
         self.keys = [k.to(device) for k in self.keys]
         for name in ("parent", "child8", "nbr27"):
             setattr(self, name, [t.to(device) if t is not None else None for t in getattr(self, name)])
+        if self.nbr125_top is not None:
+            self.nbr125_top = self.nbr125_top.to(device)
         self._view = None
         return self
