@@ -204,7 +204,7 @@ class KernelField(BaseField):
         if svh.depth > 1 and n > offs[1]:
             seg = cnt_down[offs[1]:]
             lo_b = 1
-            for cap in (32, 128, 512, 2048, 16384):
+            for cap in (32, 128, 512, 1024, 2048, 4096, 8192, 16384):
                 rows = (torch.nonzero((seg > lo_b) & (seg <= cap)).reshape(-1) + offs[1]).to(torch.int32)
                 lo_b = cap
                 if rows.numel():

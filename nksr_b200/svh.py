@@ -53,9 +53,11 @@ class SparseFeatureHierarchy:
         self.depth = depth
         self.device = torch.device(device)
         self.keys: List[torch.Tensor] = [torch.zeros(0, dtype=torch.int64, device=self.device) for _ in range(depth)]
-        self.parent: List[Optional[torch.Tensor]] = [None] * depth
-        self.child8: List[Optional[torch.Tensor]] = [None] * depth
-        self.nbr27: List[Optional[torch.Tensor]] = [None] * depth
+        # tables have one extra slot: index `depth` is the virtual level above the coarsest one
+        self.parent: List[Optional[torch.Tensor]] = [None] * (depth + 1)
+        self.child8: List[Optional[torch.Tensor]] = [None] * (depth + 1)
+        self.nbr27: List[Optional[torch.Tensor]] = [None] * (depth + 1)
+        self.top_keys: Optional[torch.Tensor] = None
         self.nbr125_top: Optional[torch.Tensor] = None
         self._view = None
 
@@ -74,32 +76,39 @@ class SparseFeatureHierarchy:
         if int(status.item()) & 1:
             raise _lib.NksrError("point coordinates outside the supported range (|x| < 2^19 voxels) or non-finite")
         keys = []
-        for l in range(self.depth):
+        # one extra, VIRTUAL level on top (no unknowns): it parents the coarsest real level so that
+        # every level finds its 125-neighbourhood through parent tables and can be grouped by parent
+        for l in range(self.depth + 1):
             cand = torch.empty(uh.numel() * 8, dtype=torch.int64, device=dev)
             call("nksr_splat_candidates", uh, uh.numel(), cand, st)
             keys.append(_lib.unique_sorted(_lib.sort_keys(cand)))
-            if l + 1 < self.depth:
+            if l < self.depth:
                 uh = _lib.unique_sorted(uh, 3)
-        return self.build_from_keys(keys)
+        return self.build_from_keys(keys[:self.depth], top_keys=keys[self.depth])
 
-    def build_from_keys(self, keys):
-        """Adopt sorted, unique, parent-closed Morton keys per level and build the tables."""
+    def build_from_keys(self, keys, top_keys=None):
+        """Adopt sorted, unique, parent-closed Morton keys per level and build the tables.
+        `top_keys`: keys of the virtual level above the coarsest one (default: its parents)."""
         self.keys = [k.to(self.device, torch.int64).contiguous() for k in keys]
         dev, st = self.device, stream_ptr(self.device)
         L = self.depth
+        if top_keys is None:
+            top_keys = _lib.unique_sorted(self.keys[L - 1], 3)
+        self.top_keys = top_keys.to(dev, torch.int64).contiguous()
+        allk = self.keys + [self.top_keys]
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        for l in range(L - 1):
-            n, nu = self.keys[l].numel(), self.keys[l + 1].numel()
+        for l in range(L):
+            n, nu = allk[l].numel(), allk[l + 1].numel()
             self.parent[l] = torch.empty(n, dtype=torch.int32, device=dev)
-            call("nksr_parent_index", self.keys[l], n, self.keys[l + 1], nu, self.parent[l], status, st)
+            call("nksr_parent_index", allk[l], n, allk[l + 1], nu, self.parent[l], status, st)
             self.child8[l + 1] = torch.empty((nu, 8), dtype=torch.int32, device=dev)
-            call("nksr_child_table", self.keys[l], self.parent[l], n, self.child8[l + 1], nu, st)
+            call("nksr_child_table", allk[l], self.parent[l], n, self.child8[l + 1], nu, st)
+        self.nbr27[L] = torch.empty((self.top_keys.numel(), 27), dtype=torch.int32, device=dev)
+        call("nksr_nbr27_search", self.top_keys, self.top_keys.numel(), self.nbr27[L], st)
         top = self.keys[L - 1]
-        self.nbr27[L - 1] = torch.empty((top.numel(), 27), dtype=torch.int32, device=dev)
-        call("nksr_nbr27_search", top, top.numel(), self.nbr27[L - 1], st)
         self.nbr125_top = torch.empty((top.numel(), 125), dtype=torch.int32, device=dev)
         call("nksr_nbr125_search", top, top.numel(), self.nbr125_top, st)
-        for l in range(L - 2, -1, -1):
+        for l in range(L - 1, -1, -1):
             n = self.keys[l].numel()
             self.nbr27[l] = torch.empty((n, 27), dtype=torch.int32, device=dev)
             call("nksr_nbr27_from_parent", self.keys[l], self.parent[l], n, self.nbr27[l + 1], self.child8[l + 1],
@@ -148,6 +157,15 @@ class SparseFeatureHierarchy:
                 v.child8[l] = self.child8[l].data_ptr() if self.child8[l] is not None else None
                 v.nbr27[l] = self.nbr27[l].data_ptr() if self.nbr27[l] is not None else None
             v.nbr125_top = self.nbr125_top.data_ptr() if self.nbr125_top is not None else None
+            L = self.depth
+            if L < _lib.MAX_DEPTH and self.top_keys is not None:          # virtual level at index L
+                v.n[L] = self.top_keys.numel()
+                v.offset[L] = offs[L]
+                v.keys[L] = self.top_keys.data_ptr()
+                v.child8[L] = self.child8[L].data_ptr()
+                v.nbr27[L] = self.nbr27[L].data_ptr()
+            else:
+                v.parent[L - 1] = None
             self._view = v
         return self._view
 
@@ -187,5 +205,7 @@ class SparseFeatureHierarchy:
             setattr(self, name, [t.to(device) if t is not None else None for t in getattr(self, name)])
         if self.nbr125_top is not None:
             self.nbr125_top = self.nbr125_top.to(device)
+        if self.top_keys is not None:
+            self.top_keys = self.top_keys.to(device)
         self._view = None
         return self
