@@ -16,6 +16,8 @@
 // and row ranges are fetched lane-parallel once per row, row pointers advance by one add per
 // level, and with approx_kernel_grad the three gradient rows are rebuilt from ONE 128-byte
 // line (<phi,z_s> + tau) with nine FMAs instead of being loaded.
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -122,7 +124,7 @@ __global__ void k_set_last(const int32_t* cnt, const int32_t* cnt_down, int64_t 
 }
 
 template <bool COMPACT, int MAXL>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, MAXL <= 4 ? 4 : 2)
 k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_total,
             const int32_t* __restrict__ cnt, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col_out,
             float* __restrict__ val_out, float* __restrict__ rhs, float* __restrict__ diag,
@@ -606,7 +608,8 @@ int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_co
   const int64_t n = total_unknowns(svh);
   if (n == 0) return NKSR_OK;
   cudaStream_t s = as_stream(stream);
-  if (svh->parent[svh->depth - 1] && svh->depth < NKSR_MAX_DEPTH) {
+  const char* variant = getenv("NKSR_FILL_VARIANT");  // "group" selects the staged kernel (A/B switch)
+  if (variant && variant[0] == 'g' && svh->parent[svh->depth - 1] && svh->depth < NKSR_MAX_DEPTH) {
     // grouped kernel: one CTA per parent voxel of every level (the virtual level parents the top)
     int64_t groups = 0;
     for (int l = 0; l < svh->depth; ++l) groups += svh->n[l + 1];
