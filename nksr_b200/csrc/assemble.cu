@@ -16,8 +16,6 @@
 // and row ranges are fetched lane-parallel once per row, row pointers advance by one add per
 // level, and with approx_kernel_grad the three gradient rows are rebuilt from ONE 128-byte
 // line (<phi,z_s> + tau) with nine FMAs instead of being loaded.
-#include <cstdlib>
-
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -283,246 +281,13 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
   if (lane == 0) rhs[row] = bsum;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Grouped numeric assembly (used whenever the hierarchy carries the virtual top level).
-// One CTA per PARENT voxel p (level l+1): its <= 8 children are the rows, one warp each.  The 27-
-// neighbourhoods of the children cover a 4x4x4 block of level-l voxels, so every constraint row
-// in that block is staged ONCE in shared memory (all eight warps issue the loads: many bytes in
-// flight, none of the per-row latency chains of the warp-per-row kernel) and, for compact
-// gradient rows, expanded once into its three gradient rows; each row-warp then consumes the
-// staged rows of the cells within its own 27-stencil with shared-memory loads only.
-constexpr int kChunk = 8;
-
-template <bool COMPACT, int MAXL>
-__global__ void __launch_bounds__(kWarps * 32, MAXL <= 4 ? 3 : 2)
-k_gram_fill_group(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, const int32_t* __restrict__ cnt,
-                  const int64_t* __restrict__ rowptr, int32_t* __restrict__ col_out, float* __restrict__ val_out,
-                  float* __restrict__ rhs, float* __restrict__ diag, int32_t* __restrict__ cursor) {
-  constexpr int SLOTS = 125 + 64 * (MAXL - 1);
-  constexpr int ESTRIDE = MAXL * 96;  // floats per staged entry: [level][3 rows][32]
-  extern __shared__ float smem[];
-  float* s_acc = smem;                   // [8][SLOTS]
-  float* s_exp = smem + kWarps * SLOTS;  // [2][kChunk][MAXL][3][32]
-  __shared__ int s_u[64], s_pb[64], s_np[64], s_nb[64], s_nn[64], s_off[65];
-  __shared__ int s_mq[3][kChunk], s_mcell[3][kChunk], s_mtype[3][kChunk];
-  __shared__ float s_t[2][kChunk][3];
-
-  int64_t b = blockIdx.x;
-  int l = 0;
-  while (l + 1 < svh.depth && b >= svh.n[l + 1]) { b -= svh.n[l + 1]; ++l; }
-  const int p = (int)b;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nup = svh.depth - 1 - l;
-  const int64_t N = cs.n_pos, K = cs.n_nrm;
-  const int32_t* rp = cs.range_pos ? cs.range_pos + 2 * svh.offset[l] : nullptr;
-  const int32_t* rn = cs.range_nrm ? cs.range_nrm + 2 * svh.offset[l] : nullptr;
-  const int i = __ldg(svh.child8[l + 1] + (int64_t)p * 8 + wid);  // this warp's row voxel, -1 = none
-
-  if (tid < 64) {
-    const int ax = tid >> 4, ay = (tid >> 2) & 3, az = tid & 3;
-    const int ex = ax == 0 ? -1 : (ax == 3 ? 1 : 0), ey = ay == 0 ? -1 : (ay == 3 ? 1 : 0),
-              ez = az == 0 ? -1 : (az == 3 ? 1 : 0);
-    const int pn = __ldg(svh.nbr27[l + 1] + (int64_t)p * 27 + (ex + 1) * 9 + (ey + 1) * 3 + (ez + 1));
-    int u = -1, pb = 0, np = 0, nb = 0, nn = 0;
-    if (pn >= 0)
-      u = __ldg(svh.child8[l + 1] + (int64_t)pn * 8 + ((((ax + 1) & 1) << 2) | (((ay + 1) & 1) << 1) | ((az + 1) & 1)));
-    if (u >= 0) {
-      if (rp) { pb = __ldg(rp + 2 * (int64_t)u); np = __ldg(rp + 2 * (int64_t)u + 1) - pb; }
-      if (rn) { nb = __ldg(rn + 2 * (int64_t)u); nn = __ldg(rn + 2 * (int64_t)u + 1) - nb; }
-    }
-    s_u[tid] = u; s_pb[tid] = pb; s_np[tid] = np; s_nb[tid] = nb; s_nn[tid] = nn;
-  }
-  for (int t = tid; t < kWarps * SLOTS; t += kWarps * 32) s_acc[t] = 0.f;
-  __syncthreads();
-  if (tid < 64) {
-    int off = 0;
-    for (int j = 0; j < tid; ++j) off += s_np[j] + s_nn[j];
-    s_off[tid] = off;
-    if (tid == 63) s_off[64] = off + s_np[63] + s_nn[63];
-  }
-  __syncthreads();
-  const int T = s_off[64];
-
-  // per-entry metadata of chunk `ci` (entries [ci*kChunk, ...)) into slot ci % 3
-  auto make_meta = [&](int ci) {
-    const int ge = ci * kChunk + tid;
-    if (tid < kChunk && ge < T) {
-      int lo = 0, hi = 64;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_off[mid] <= ge) lo = mid; else hi = mid;
-      }
-      const int j = ge - s_off[lo];
-      const bool isn = j >= s_np[lo];
-      s_mcell[ci % 3][tid] = lo;
-      s_mtype[ci % 3][tid] = isn ? 1 : 0;
-      s_mq[ci % 3][tid] = isn ? s_nb[lo] + j - s_np[lo] : s_pb[lo] + j;
-    }
-  };
-  make_meta(0);
-  __syncthreads();
-
-  RowGeom g;
-  g.ux = g.uy = g.uz = 0;
-#pragma unroll
-  for (int k = 0; k < NKSR_MAX_DEPTH; ++k) g.anc[k] = -1;
-  if (i >= 0) {
-    morton3_decode(__ldg(svh.keys[l] + i), g.ux, g.uy, g.uz);
-    g.anc[0] = i;
-    int a = p;
-#pragma unroll
-    for (int k = 1; k < NKSR_MAX_DEPTH; ++k) {
-      if (l + k < svh.depth) { g.anc[k] = a; a = (a >= 0 && l + k + 1 < svh.depth) ? __ldg(svh.parent[l + k] + a) : -1; }
-    }
-  }
-  const int sl = lane < 27 ? lane : 13;
-  const int ldx = c_d27[sl][0], ldy = c_d27[sl][1], ldz = c_d27[sl][2];
-  const float cx0 = ldx == 0 ? 0.75f : 0.125f, cx1 = 0.5f * (float)ldx, cx2 = ldx == 0 ? -1.f : 0.5f;
-  const float cy0 = ldy == 0 ? 0.75f : 0.125f, cy1 = 0.5f * (float)ldy, cy2 = ldy == 0 ? -1.f : 0.5f;
-  const float cz0 = ldz == 0 ? 0.75f : 0.125f, cz1 = 0.5f * (float)ldz, cz2 = ldz == 0 ? -1.f : 0.5f;
-  const float inv_wl = 1.f / (svh.voxel_size * (float)(1 << l));
-  const int ccx = (wid >> 2) & 1, ccy = (wid >> 1) & 1, ccz = wid & 1;  // child position of this row
-  float* acc = s_acc + wid * SLOTS;
-  float r[MAXL];
-#pragma unroll
-  for (int k = 0; k < MAXL; ++k) r[k] = 0.f;
-  float bsum = 0.f;
-  int cur_cell = -1, si = 0, udx = 0, udy = 0, udz = 0;
-  bool member = false;
-
-  auto flush = [&]() {
-    if (member && lane < 27) {
-      acc[(udx + ldx + 2) * 25 + (udy + ldy + 2) * 5 + (udz + ldz + 2)] += r[0];
-      const int vx = g.ux + udx, vy = g.uy + udy, vz = g.uz + udz;
-#pragma unroll
-      for (int k = 1; k < MAXL; ++k) {
-        if (k <= nup) {
-          const int ox = ((vx >> k) + ldx) - (((g.ux - 1) >> k) - 1);
-          const int oy = ((vy >> k) + ldy) - (((g.uy - 1) >> k) - 1);
-          const int oz = ((vz >> k) + ldz) - (((g.uz - 1) >> k) - 1);
-          acc[125 + 64 * (k - 1) + (ox << 4) + (oy << 2) + oz] += r[k];
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < MAXL; ++k) r[k] = 0.f;
-  };
-
-  const int nlev = nup + 1;
-  for (int c0 = 0, it = 0; c0 < T; c0 += kChunk, ++it) {
-    const int buf = it & 1, mb = it % 3;
-    make_meta(it + 1);
-    const int ne = min(kChunk, T - c0);
-    // ---- stage: one warp per (entry, level) line
-    for (int ln = wid; ln < ne * nlev; ln += kWarps) {
-      const int e = ln / nlev, k = ln - e * nlev;
-      const int q = s_mq[mb][e];
-      float* dst = s_exp + ((size_t)(buf * kChunk + e) * MAXL + k) * 96;
-      if (!s_mtype[mb][e]) {
-        dst[lane] = __ldg(cs.e_pos + ((int64_t)(l + k) * N + q) * NKSR_ROW_STRIDE + lane);
-      } else if (COMPACT) {
-        const float line = __ldg(cs.e_nrm + ((int64_t)(l + k) * K + q) * NKSR_ROW_STRIDE + lane);
-        const float tx = __shfl_sync(0xffffffffu, line, 27), ty = __shfl_sync(0xffffffffu, line, 28),
-                    tz = __shfl_sync(0xffffffffu, line, 29);
-        const float bx = fmaf(fmaf(cx2, tx, cx1), tx, cx0), dbx = fmaf(2.f * cx2, tx, cx1);
-        const float by = fmaf(fmaf(cy2, ty, cy1), ty, cy0), dby = fmaf(2.f * cy2, ty, cy1);
-        const float bz = fmaf(fmaf(cz2, tz, cz1), tz, cz0), dbz = fmaf(2.f * cz2, tz, cz1);
-        const float sc = (lane < 27 ? line : 0.f) * (inv_wl / (float)(1 << k));
-        dst[lane] = dbx * by * bz * sc;
-        dst[32 + lane] = bx * dby * bz * sc;
-        dst[64 + lane] = bx * by * dbz * sc;
-        if (k == 0 && lane < 3) s_t[buf][e][lane] = __ldg(cs.t_nrm + (int64_t)q * 3 + lane);
-      } else {
-        const float* src = cs.e_nrm + ((int64_t)(l + k) * K + q) * (3 * NKSR_ROW_STRIDE);
-        dst[lane] = __ldg(src + lane);
-        dst[32 + lane] = __ldg(src + 32 + lane);
-        dst[64 + lane] = __ldg(src + 64 + lane);
-        if (k == 0 && lane < 3) s_t[buf][e][lane] = __ldg(cs.t_nrm + (int64_t)q * 3 + lane);
-      }
-    }
-    __syncthreads();
-    // ---- consume
-    if (i >= 0) {
-      for (int e = 0; e < ne; ++e) {
-        const int cell = s_mcell[mb][e];
-        if (cell != cur_cell) {
-          flush();
-          cur_cell = cell;
-          udx = (cell >> 4) - 1 - ccx; udy = ((cell >> 2) & 3) - 1 - ccy; udz = (cell & 3) - 1 - ccz;
-          member = udx >= -1 && udx <= 1 && udy >= -1 && udy <= 1 && udz >= -1 && udz <= 1;
-          si = 26 - ((udx + 1) * 9 + (udy + 1) * 3 + (udz + 1));
-        }
-        if (!member) continue;
-        const float* ex = s_exp + (size_t)(buf * kChunk + e) * ESTRIDE;
-        if (!s_mtype[mb][e]) {
-          const float a = cs.w_pos * ex[si];
-#pragma unroll
-          for (int k = 0; k < MAXL; ++k)
-            if (k <= nup) r[k] = fmaf(a, ex[k * 96 + lane], r[k]);
-        } else {
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) {
-            const float a = cs.w_nrm * ex[ax * 32 + si];
-            bsum = fmaf(a, s_t[buf][e][ax], bsum);
-#pragma unroll
-            for (int k = 0; k < MAXL; ++k)
-              if (k <= nup) r[k] = fmaf(a, ex[k * 96 + ax * 32 + lane], r[k]);
-          }
-        }
-      }
-    }
-  }
-  flush();
-  if (i < 0) return;
-  __syncwarp();
-  const int64_t row = svh.offset[l] + i;
-  // regulariser: R_{i,i+d} = w_reg * B3(d) * <z_i, z_{i+d}>  (SPEC S5)
-  if (cs.w_reg != 0.f && lane < 27) {
-    const int nbv = __ldg(svh.nbr27[l] + (int64_t)i * 27 + lane);
-    if (nbv >= 0) {
-      const int C = feat.channels;
-      const float* zi = feat.z[l] + (int64_t)i * C;
-      const float* zn = feat.z[l] + (int64_t)nbv * C;
-      float d = 0.f;
-      for (int c = 0; c < C; ++c) d = fmaf(__ldg(zi + c), __ldg(zn + c), d);
-      const float bw = (ldx == 0 ? 0.75f : 0.125f) * (ldy == 0 ? 0.75f : 0.125f) * (ldz == 0 ? 0.75f : 0.125f);
-      acc[(ldx + 2) * 25 + (ldy + 2) * 5 + (ldz + 2)] += cs.w_reg * bw * d;
-    }
-  }
-  __syncwarp();
-  const int nslots = 125 + 64 * nup;
-  const int64_t p0 = rowptr[row];
-  int written = 0;
-  for (int t0 = 0; t0 < nslots; t0 += 32) {
-    const int t = t0 + lane;
-    int k = 0;
-    const int c = t < nslots ? slot_column(svh, l, g, t, k) : -1;
-    const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
-    if (c >= 0) {
-      const int64_t pp = p0 + written + __popc(m & ((1u << lane) - 1u));
-      const float v = acc[t];
-      const int64_t gc = svh.offset[l + k] + c;
-      col_out[pp] = (int32_t)gc;
-      val_out[pp] = v;
-      if (k == 0 && c == i) diag[row] = v;
-      if (k > 0) {
-        const int64_t q = rowptr[gc] + cnt[gc] + atomicAdd(cursor + gc, 1);
-        col_out[q] = (int32_t)row;
-        val_out[q] = v;
-      }
-    }
-    written += __popc(m);
-  }
-  if (lane == 0) rhs[row] = bsum;
-}
-
-// bitonic sort of the finer-level segment of each listed row by column (block per row)
+// Sort of the finer-level (transposed) segment of each listed row by column.  (column, value)
+// pairs are packed into one 64-bit word (column in the high half) so a compare-exchange is one
+// 8-byte shared-memory access per side; every thread owns a compare-exchange pair (no idle half).
 __global__ void k_sort_down(const int32_t* __restrict__ cnt, const int32_t* __restrict__ cnt_down,
                             const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rows, int64_t n_rows,
                             int32_t* __restrict__ col, float* __restrict__ val, int cap) {
-  extern __shared__ unsigned char raw[];
-  int32_t* sc = reinterpret_cast<int32_t*>(raw);
-  float* sv = reinterpret_cast<float*>(raw) + cap;
+  extern __shared__ unsigned long long skey[];
   if (blockIdx.x >= n_rows) return;
   const int64_t row = rows[blockIdx.x];
   const int m = cnt_down[row];
@@ -530,30 +295,55 @@ __global__ void k_sort_down(const int32_t* __restrict__ cnt, const int32_t* __re
   const int64_t p0 = rowptr[row] + cnt[row];
   int m2 = 1;
   while (m2 < m) m2 <<= 1;
-  for (int t = threadIdx.x; t < m2; t += blockDim.x) {
-    sc[t] = t < m ? col[p0 + t] : 0x7fffffff;
-    sv[t] = t < m ? val[p0 + t] : 0.f;
-  }
+  for (int t = threadIdx.x; t < m2; t += blockDim.x)
+    skey[t] = t < m ? (((unsigned long long)(unsigned)col[p0 + t] << 32) | __float_as_uint(val[p0 + t]))
+                    : 0xffffffffffffffffull;
   __syncthreads();
+  const int half = m2 >> 1;
   for (int k = 2; k <= m2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < m2; t += blockDim.x) {
-        const int p = t ^ j;
-        if (p > t) {
-          const bool up = (t & k) == 0;
-          const int a = sc[t], b = sc[p];
-          if ((a > b) == up) {
-            sc[t] = b; sc[p] = a;
-            const float x = sv[t]; sv[t] = sv[p]; sv[p] = x;
-          }
-        }
+      for (int q = threadIdx.x; q < half; q += blockDim.x) {
+        const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+        const int hi = lo | j;
+        const unsigned long long a = skey[lo], b = skey[hi];
+        if ((a > b) == ((lo & k) == 0)) { skey[lo] = b; skey[hi] = a; }
       }
       __syncthreads();
     }
   }
   for (int t = threadIdx.x; t < m; t += blockDim.x) {
-    col[p0 + t] = sc[t];
-    val[p0 + t] = sv[t];
+    const unsigned long long v = skey[t];
+    col[p0 + t] = (int32_t)(v >> 32);
+    val[p0 + t] = __uint_as_float((unsigned)v);
+  }
+}
+
+// segments of at most 32 entries: one warp per row, bitonic network through shuffles
+__global__ void k_sort_down_warp(const int32_t* __restrict__ cnt, const int32_t* __restrict__ cnt_down,
+                                 const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rows,
+                                 int64_t n_rows, int32_t* __restrict__ col, float* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int64_t row = rows[r];
+  const int m = cnt_down[row];
+  if (m <= 1 || m > 32) return;
+  const int64_t p0 = rowptr[row] + cnt[row];
+  unsigned long long key = lane < m ? (((unsigned long long)(unsigned)col[p0 + lane] << 32) |
+                                       __float_as_uint(val[p0 + lane]))
+                                    : 0xffffffffffffffffull;
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+      key = keep_min ? (key < other ? key : other) : (key > other ? key : other);
+    }
+  }
+  if (lane < m) {
+    col[p0 + lane] = (int32_t)(key >> 32);
+    val[p0 + lane] = __uint_as_float((unsigned)key);
   }
 }
 
@@ -608,30 +398,6 @@ int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_co
   const int64_t n = total_unknowns(svh);
   if (n == 0) return NKSR_OK;
   cudaStream_t s = as_stream(stream);
-  const char* variant = getenv("NKSR_FILL_VARIANT");  // "group" selects the staged kernel (A/B switch)
-  if (variant && variant[0] == 'g' && svh->parent[svh->depth - 1] && svh->depth < NKSR_MAX_DEPTH) {
-    // grouped kernel: one CTA per parent voxel of every level (the virtual level parents the top)
-    int64_t groups = 0;
-    for (int l = 0; l < svh->depth; ++l) groups += svh->n[l + 1];
-    if (groups <= 0 || groups > 0x7fffffff) return NKSR_E_INVALID;
-#define NKSR_FILLG(COMPACT, MAXL)                                                                              \
-  do {                                                                                                         \
-    const size_t sm = (size_t)(kWarps * (125 + 64 * (MAXL - 1)) + 2 * kChunk * MAXL * 96) * sizeof(float);     \
-    if (cudaFuncSetAttribute(k_gram_fill_group<COMPACT, MAXL>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                             (int)sm) != cudaSuccess)                                                         \
-      return NKSR_E_CUDA;                                                                                      \
-    k_gram_fill_group<COMPACT, MAXL><<<(unsigned)groups, kWarps * 32, sm, s>>>(*svh, *feat, *c, cnt, rowptr,   \
-                                                                               col, val, rhs, diag, cursor);  \
-  } while (0)
-    if (svh->depth <= 4) {
-      if (c->nrm_compact) NKSR_FILLG(true, 4); else NKSR_FILLG(false, 4);
-    } else {
-      if (c->nrm_compact) NKSR_FILLG(true, NKSR_MAX_DEPTH); else NKSR_FILLG(false, NKSR_MAX_DEPTH);
-    }
-#undef NKSR_FILLG
-    NKSR_CHECK_LAUNCH();
-    return NKSR_OK;
-  }
   const size_t smem = (size_t)kWarps * kMaxSlots * sizeof(float);
   const int grid = grid_for(n, kWarps);
 #define NKSR_FILL(COMPACT, MAXL) \
@@ -655,9 +421,14 @@ int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, const int64
   if (cap * 8 > 48 * 1024 &&
       cudaFuncSetAttribute(k_sort_down, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8) != cudaSuccess)
     return NKSR_E_CUDA;
-  const int threads = cap >= 2048 ? 256 : (cap >= 256 ? 128 : 32);
-  k_sort_down<<<(unsigned)n_rows, threads, cap * 8, as_stream(stream)>>>(cnt, cnt_down, rowptr, rows, n_rows, col,
-                                                                         val, cap);
+  if (cap <= 32) {
+    k_sort_down_warp<<<grid_for(n_rows, 8), 256, 0, as_stream(stream)>>>(cnt, cnt_down, rowptr, rows, n_rows, col,
+                                                                        val);
+  } else {
+    const int threads = cap >= 4096 ? 512 : (cap >= 1024 ? 256 : (cap >= 256 ? 128 : 64));
+    k_sort_down<<<(unsigned)n_rows, threads, cap * 8, as_stream(stream)>>>(cnt, cnt_down, rowptr, rows, n_rows, col,
+                                                                           val, cap);
+  }
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

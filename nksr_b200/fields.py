@@ -169,7 +169,10 @@ class KernelField(BaseField):
             normal_xyz = normal_xyz.detach().to(dev, torch.float32).contiguous()
             normal_value = normal_value.detach().to(dev, torch.float32).contiguous()
             # approx_kernel_grad: compact gradient rows (one 128 B line per location and level)
-            nrm_mode = 2 if (self.approx_kernel_grad and self.solver_config.get("compact_rows", True)) else 1
+            # compact gradient rows (one line instead of three per location and level) save 2/3 of
+            # the row memory but cost ALU in the assembly; measured slower on B200 (profiles/r1c),
+            # so they are opt-in for clouds that would not fit otherwise
+            nrm_mode = 2 if (self.approx_kernel_grad and self.solver_config.get("compact_rows", False)) else 1
             _, t_nrm, _, range_nrm, e_nrm = self._sorted_rows(normal_xyz, nrm_mode, normal_value)
             cs.nrm_compact = int(nrm_mode == 2)
             keep += [t_nrm, range_nrm, e_nrm]

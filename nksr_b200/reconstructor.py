@@ -194,6 +194,8 @@ class Reconstructor:
         tm.mark("network")
         field.solver_config["tol"] = float(solver_tol)
         field.solver_config["max_iter"] = int(solver_max_iter)
+        # large systems: an iteration costs milliseconds, so test convergence every iteration
+        field.solver_config["check_every"] = 1 if dec_svh.num_unknowns > 1_000_000 else 10
         ad = min(self.adaptive_depth, dec_svh.depth)
         normal_xyz = torch.cat([dec_svh.get_voxel_centers(d) for d in range(ad)])
         normal_value = torch.cat([feats.normal_features[d] for d in range(ad)])
