@@ -98,8 +98,11 @@ NKSR_API int nksr_pool27(const int32_t* nbr27, const float* in, int64_t n, int c
 NKSR_API int nksr_row_ranges(const int32_t* base_l, int64_t m, int32_t* range, int64_t n_l, void* stream);
 
 /* ---- a3: KernelField.solve* Gram assembly (models/nksr_net.py:100-112) ---- */
-/* kernel rows. mode 0: value rows  e[(l*M + m)*32 + s]            (position constraints)
- *              mode 1: gradient rows e[((l*M + m)*3 + a)*32 + s]  (normal constraints)   */
+/* kernel rows, location-major (all lines of one location are contiguous):
+ *   mode 0: value rows    e[(m*L + l)*32 + s]             (position constraints)
+ *   mode 1: gradient rows e[((m*L + l)*3 + a)*32 + s]     (normal constraints)
+ *   mode 2: compact gradient rows e[(m*L + l)*32 + s], s<27: <phi,z_s>, s=27..29: tau
+ *           (approx_kernel_grad only; the assembly rebuilds the three rows)              */
 NKSR_API int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* xyz,
                     const int32_t* base, int64_t m, int mode, int approx_kernel_grad, float* e,
                     void* stream);
@@ -110,17 +113,17 @@ NKSR_API size_t nksr_scan_workspace_bytes(int64_t n);
 NKSR_API int nksr_gram_rowptr(const int32_t* cnt, const int32_t* cnt_down, int64_t n, int64_t* rowptr,
                      void* ws, size_t ws_bytes, void* stream);
 typedef struct {
-  const float* e_pos;        /* value rows of the N sorted positions  [L][N][32]      */
+  const float* e_pos;        /* value rows of the N sorted positions  [N][L][32]      */
   const int32_t* range_pos;  /* per level [n_l][2] (concatenated in level order)      */
   int64_t n_pos;
   float w_pos;
-  const float* e_nrm;        /* gradient rows of the K sorted normal locations [L][K][3][32] */
+  const float* e_nrm;        /* gradient rows of the K sorted normal locations [K][L][3][32] */
   const int32_t* range_nrm;
   const float* t_nrm;        /* [K][3] targets (sorted order)                          */
   int64_t n_nrm;
   float w_nrm;
   float w_reg;
-  int32_t nrm_compact;       /* 1: e_nrm holds compact rows [L][K][32] (nksr_build_rows mode 2) */
+  int32_t nrm_compact;       /* 1: e_nrm holds compact rows [K][L][32] (nksr_build_rows mode 2) */
 } nksr_constraints_t;
 /* numeric assembly: fills col/val (CSR, int64 rowptr), rhs b, diag. cursor[n] must be zero. */
 NKSR_API int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c,

@@ -130,8 +130,10 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
-  const int64_t row = blockIdx.x * (int64_t)kWarps + wid;
-  if (row >= n_total) return;
+  // coarse rows own thousands of constraint rows, fine rows a few dozen: schedule the heavy
+  // (coarse, high index) rows first so that the tail of the grid is made of light rows
+  const int64_t row = n_total - 1 - (blockIdx.x * (int64_t)kWarps + wid);
+  if (row < 0) return;
   int l, i;
   row_of_warp(svh, row, l, i);
   const int L = svh.depth;
@@ -160,8 +162,10 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
   const float cy0 = ldy == 0 ? 0.75f : 0.125f, cy1 = 0.5f * (float)ldy, cy2 = ldy == 0 ? -1.f : 0.5f;
   const float cz0 = ldz == 0 ? 0.75f : 0.125f, cz1 = 0.5f * (float)ldz, cz2 = ldz == 0 ? -1.f : 0.5f;
   const float inv_wl = 1.f / (svh.voxel_size * (float)(1 << l));
-  const int64_t pos_level = N * NKSR_ROW_STRIDE;
-  const int64_t nrm_level = K * NKSR_ROW_STRIDE * (COMPACT ? 1 : 3);
+  // rows are stored location-major ([q][L][rows][32]): level stride is a compile-time constant
+  constexpr int pos_level = NKSR_ROW_STRIDE;
+  constexpr int nrm_level = NKSR_ROW_STRIDE * (COMPACT ? 1 : 3);
+  (void)N; (void)K;
   __syncwarp();
 
   for (int us = 0; us < 27; ++us) {
@@ -175,7 +179,7 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
 #pragma unroll
     for (int k = 0; k < MAXL; ++k) r[k] = 0.f;
     for (int q = pb; q < pe; ++q) {
-      const float* p0 = cs.e_pos + ((int64_t)l * N + q) * NKSR_ROW_STRIDE;
+      const float* p0 = cs.e_pos + ((int64_t)q * L + l) * NKSR_ROW_STRIDE;
       const float a = cs.w_pos * __ldg(p0 + si);
       const float* pk = p0 + lane;
 #pragma unroll
@@ -186,7 +190,7 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
       // one line per (location, level): <phi,z_s> in slots 0..26, tau in 27..29;
       // E_a[s] = dB_a B_b B_c <phi,z_s> / W_level
       for (int q = nb; q < ne; ++q) {
-        const float* pk = cs.e_nrm + ((int64_t)l * K + q) * NKSR_ROW_STRIDE + lane;
+        const float* pk = cs.e_nrm + ((int64_t)q * L + l) * NKSR_ROW_STRIDE + lane;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, iw = inv_wl;
 #pragma unroll
         for (int k = 0; k < MAXL; ++k) {
@@ -214,7 +218,7 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
       }
     } else {
       for (int q = nb; q < ne; ++q) {
-        const float* p0 = cs.e_nrm + ((int64_t)l * K + q) * (3 * NKSR_ROW_STRIDE);
+        const float* p0 = cs.e_nrm + ((int64_t)q * L + l) * (3 * NKSR_ROW_STRIDE);
         const float* t = cs.t_nrm + (int64_t)q * 3;
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) {

@@ -23,7 +23,9 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
   const int64_t i = warp - (int64_t)l * m;
   const int b = __ldg(base + (int64_t)l * m + i);
   constexpr bool GRAD = MODE == 1;
-  float* out = e + (GRAD ? ((int64_t)l * m + i) * 3 * NKSR_ROW_STRIDE : ((int64_t)l * m + i) * NKSR_ROW_STRIDE);
+  // location-major layout [m][L][rows][32]: all lines of one location are contiguous, so the
+  // assembly kernel reaches them with compile-time offsets from one base pointer
+  float* out = e + ((int64_t)i * svh.depth + l) * (GRAD ? 3 : 1) * NKSR_ROW_STRIDE;
   if (b < 0) {
     out[lane] = 0.f;
     if (GRAD) { out[32 + lane] = 0.f; out[64 + lane] = 0.f; }

@@ -142,7 +142,7 @@ class KernelField(BaseField):
         for l in range(svh.depth):
             call("nksr_row_ranges", base[l], m, ranges[offs[l]:], svh.num_voxels(l), st)
         width = _lib.ROW_STRIDE * (3 if mode == 1 else 1)
-        e = torch.empty((svh.depth, m, width), dtype=torch.float32, device=dev)
+        e = torch.empty((m, svh.depth, width), dtype=torch.float32, device=dev)      # location-major
         call("nksr_build_rows", svh.view(), self.feat_view(), xs, base, m, mode,
              int(self.approx_kernel_grad), e, st)
         return xs, ex, base, ranges, e

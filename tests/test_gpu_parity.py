@@ -84,12 +84,12 @@ def test_kernel_rows_match_oracle(cuda, C, approx):
         for l in range(4):
             nbr, K, dK = O.level_rows(osvh, l, xs_np, base_np[l], feats[l], mode == 1, approx)
             if mode == 0:
-                got, ref = e_np[l][:, :27], K
+                got, ref = e_np[:, l, :27], K
             else:
-                got, ref = e_np[l].reshape(-1, 3, 32)[:, :, :27], dK
+                got, ref = e_np[:, l].reshape(-1, 3, 32)[:, :, :27], dK
             scale = np.abs(ref).max()
             assert np.abs(got - ref).max() <= RTOL_ROW * scale, (mode, l)
-            assert np.all(e_np[l].reshape(-1, 32)[:, 27:] == 0)
+            assert np.all(e_np[:, l].reshape(-1, 32)[:, 27:] == 0)
 
 
 def _solve_setup(cuda, C=4, approx=False, n_pts=3000, W=0.02, L=4, cloud="shapenet"):
@@ -274,3 +274,36 @@ def test_normal_estimation_preprocess(cuda):
 
 def radial_full(xyz):
     return xyz / np.linalg.norm(xyz, axis=1, keepdims=True)
+
+
+def test_neural_field_mask_and_texture(cuda):
+    """NeuralField(svh, decoder, features).set_level_set + PCNNField texture (models/nksr_net.py:114-130,
+    examples/recons_colored_mesh.py:28-31): interpolation weights are checked against the oracle's tent
+    weights through a linear decoder; colours follow the nearest input point."""
+    import nksr_b200
+    field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda, 4, False, 4000, 0.05, 3, "sphere")
+    nval = -(nxyz / np.linalg.norm(nxyz, axis=1, keepdims=True)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    field.solve(t(xyz), t(nxyz), t(nval), pw, nw, rw)
+    # features = voxel centre x-coordinate on level 0 only -> trilinear interpolation reproduces x
+    f0 = svh.get_voxel_centers(0)[:, :1].contiguous()
+    dec = torch.nn.Linear(1, 1, bias=False).to(cuda)
+    with torch.no_grad():
+        dec.weight.fill_(1.0)
+    nf = nksr_b200.NeuralField(svh, dec, {0: f0})
+    q = t((xyz[:500] + 0.004).astype(np.float32))
+    got = nf.evaluate_f(q).value
+    assert torch.allclose(got, q[:, 0], atol=2e-5)
+    nf.set_level_set(0.0)                       # keep x <= 0 only
+    field.set_mask_field(nf)
+    mesh = field.extract_dual_mesh(mise_iter=1)
+    assert mesh.v.shape[0] > 100 and float(mesh.v[:, 0].max()) <= 1e-4
+    # texture: colour = nearest input point's colour
+    col = torch.rand(xyz.shape[0], 3, device=cuda)
+    field.set_texture_field(nksr_b200.PCNNField(t(xyz), col))
+    mesh = field.extract_dual_mesh()
+    d = torch.cdist(mesh.v[:200], t(xyz))
+    assert torch.equal(mesh.c[:200], col[d.argmin(dim=1)])
+    # evaluate_f_bar: masked-out side reads as outside
+    fb = field.evaluate_f_bar(t(np.array([[0.3, 0.0, 0.0], [-0.3, 0.0, 0.0]], np.float32)))
+    assert fb[0] <= 0 and fb[1] > 0
