@@ -194,7 +194,8 @@ def cpu_baseline_subprocess(workload, sample_points, timeout_s=420):
            "--workload", workload, "--cpu-sample", str(sample_points)]
     try:
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s,
-                             env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+                             env=dict(os.environ, RANK="0", WORLD_SIZE="1", OMP_NUM_THREADS="1",
+                                      OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1"))
         for line in reversed(res.stdout.strip().splitlines()):
             if line.startswith("{"):
                 return json.loads(line)["cpu_baseline"]
@@ -223,11 +224,14 @@ def cpu_baseline(workload, sample_points, cores, seed=4):
         idx = np.argpartition(d, per)[:per]
         jobs.append((xyz[idx].copy(), None, W, 4))
     # spawn (not fork): the parent holds torch/OpenMP threads; workers start before the clock does
+    print(f"[cpu_baseline] {cores} workers x {per} points; crops ready", file=sys.stderr, flush=True)
     with mp.get_context("spawn").Pool(cores) as pool:
         pool.map(_noop, range(cores))
+        print("[cpu_baseline] workers warm", file=sys.stderr, flush=True)
         t0 = time.perf_counter()
         out = pool.map(_cpu_reconstruct_chunk, jobs)
         wall = time.perf_counter() - t0
+    print(f"[cpu_baseline] done in {wall:.1f} s", file=sys.stderr, flush=True)
     pts = sum(o[0] for o in out)
     return pts / wall, pts, wall, out
 
@@ -236,7 +240,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    # one single-threaded worker per core: keep BLAS/OpenMP from oversubscribing the host
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(var, "1")
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     workload = args.workload
     vals = []
     for s in range(args.warmup + args.steps):

@@ -69,12 +69,16 @@ def get_estimate_normal_preprocess_fn(knn: int = 64, max_angle_deg: float = 85.0
         # voxel size such that a 27-neighbourhood holds ~knn points
         ext = float((xyz.max(dim=0).values - xyz.min(dim=0).values).max().item())
         lo, hi = max(ext * 1e-5, 1e-9), max(ext, 1e-6)
-        for _ in range(20):
+        for _ in range(12):                                         # log-bisection to ~0.3 %
             mid = math.sqrt(lo * hi)
-            if n / max(_count_voxels(xyz, mid), 1) * 9.0 > knn:     # ~9 occupied voxels of 27 on a surface
+            ratio = n / max(_count_voxels(xyz, mid), 1) * 9.0       # ~9 occupied voxels of 27 on a surface
+            if ratio > knn:
                 hi = mid
             else:
                 lo = mid
+            if abs(ratio - knn) < 0.05 * knn:
+                lo = hi = mid
+                break
         h = float(torch.tensor(math.sqrt(lo * hi), dtype=torch.float32).item())
         dev, st = xyz.device, stream_ptr(xyz.device)
         # Morton-sort the points so that every voxel owns one contiguous range
