@@ -275,6 +275,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mesh", action="store_true", help="also time extract_dual_mesh(mise_iter=1) (reported separately)")
     args = ap.parse_args()
+    # watchdog: a hung run prints every thread's stack to stderr and exits instead of eating the GPU lease
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("NKSR_BENCH_WATCHDOG", "1500")), exit=True)
     if args.impl == "reference":
         return run_reference(args)
 
