@@ -180,6 +180,14 @@ def _cpu_reconstruct_chunk(args):
     return xyz.shape[0], time.perf_counter() - t0, it, int(A.nnz), int(A.shape[0])
 
 
+_T0 = time.time()
+
+
+def _log(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def _noop(_):
     import numpy  # noqa: F401  (warm the worker: imports happen outside the timed region)
     import scipy.sparse  # noqa: F401
@@ -285,7 +293,9 @@ def main():
     cpu_rec = None
     if not args.no_cpu_baseline and int(os.environ.get("RANK", "0")) == 0 and \
             int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        _log("cpu baseline (subprocess) ...")
         cpu_rec = cpu_baseline_subprocess(args.workload, args.cpu_sample)
+        _log(f"cpu baseline done: {cpu_rec.get('value')}")
 
     import torch
     import torch.distributed as dist
@@ -310,6 +320,7 @@ def main():
     for s in range(n_clouds):
         xyz, sensor = make_cloud(args.workload, 4 + s, tile=rank, points=n_pts)
         host.append((xyz.pin_memory(), sensor.pin_memory()))
+    _log("clouds ready")
     rec = nksr_b200.Reconstructor(dev)
     prep = nksr_b200.get_estimate_normal_preprocess_fn(64, 85.0)
     launches = {"n": 0}
@@ -332,6 +343,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm ("value")
+    _log("device arm ...")
     dev_inputs = [(h[0].to(dev), h[1].to(dev)) for h in host]
     for s in range(args.warmup):
         f = step(*dev_inputs[s % n_clouds])
@@ -353,6 +365,7 @@ def main():
     ms_dev = ev0.elapsed_time(ev1)
     gpu_launches = launches["n"] + pcg_launch
     # ---- end-to-end arm: pinned host -> device -> reconstruct -> coefficients back to host
+    _log("e2e arm ...")
     del dev_inputs
     alpha_host = None
     barrier()
@@ -371,6 +384,7 @@ def main():
     ms_e2e = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     # ---- roofline of the dominant kernel: SpMV inside PCG, CUDA events on the launch stream
+    _log("profiled run ...")
     rec_prof = nksr_b200.Reconstructor(dev, network=rec.network)
     orig_init = nksr_b200.fields.KernelField.__init__
 
