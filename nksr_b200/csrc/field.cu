@@ -11,38 +11,45 @@ constexpr int kWarpsPerBlock = 8;
 // (MODE 1) or one compact gradient row (MODE 2, approx_kernel_grad only): slots 0..26 hold
 // <phi(x), z_s>, slots 27..29 the local coordinate tau -- the three gradient rows
 // dB_a B_b B_c <phi,z_s> / W_l are rebuilt from it inside the assembly kernel.
-template <int MODE>
+// One warp per LOCATION, all levels in one (unrolled) loop: the point is read once, the per-level
+// dependent chains (base -> key -> neighbours -> features) of the levels overlap, and the grid
+// has L times fewer blocks than a warp per (location, level).
+template <int MODE, int MAXL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, const int32_t* __restrict__ base,
              int64_t m, bool fullgrad, float* __restrict__ e) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t total = m * svh.depth;
-  if (warp >= total) return;
-  const int l = (int)(warp / m);
-  const int64_t i = warp - (int64_t)l * m;
-  const int b = __ldg(base + (int64_t)l * m + i);
+  const int64_t i = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= m) return;
   constexpr bool GRAD = MODE == 1;
+  constexpr int ROWS = GRAD ? 3 : 1;
+  const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
   // location-major layout [m][L][rows][32]: all lines of one location are contiguous, so the
   // assembly kernel reaches them with compile-time offsets from one base pointer
-  float* out = e + ((int64_t)i * svh.depth + l) * (GRAD ? 3 : 1) * NKSR_ROW_STRIDE;
-  if (b < 0) {
-    out[lane] = 0.f;
-    if (GRAD) { out[32 + lane] = 0.f; out[64 + lane] = 0.f; }
-    return;
-  }
-  const float wl = svh.voxel_size * (float)(1 << l);
-  LaneKernel r = eval_level_lane<GRAD>(svh.keys[l], svh.nbr27[l], feat.z[l], feat.channels, l, wl,
-                                       __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), b,
-                                       fullgrad, lane);
-  if (GRAD) {
-    out[lane] = r.dk[0];
-    out[32 + lane] = r.dk[1];
-    out[64 + lane] = r.dk[2];
-  } else if (MODE == 2) {
-    out[lane] = lane < 27 ? r.dot : (lane < 30 ? r.tau[lane - 27] : 0.f);
-  } else {
-    out[lane] = r.k;
+  float* out0 = e + (int64_t)i * svh.depth * ROWS * NKSR_ROW_STRIDE;
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l) {
+    if (l < svh.depth) {
+      float* out = out0 + l * ROWS * NKSR_ROW_STRIDE;
+      const int b = __ldg(base + (int64_t)l * m + i);
+      if (b < 0) {
+        out[lane] = 0.f;
+        if (GRAD) { out[32 + lane] = 0.f; out[64 + lane] = 0.f; }
+      } else {
+        const float wl = svh.voxel_size * (float)(1 << l);
+        LaneKernel r = eval_level_lane<GRAD>(svh.keys[l], svh.nbr27[l], feat.z[l], feat.channels, l, wl, px, py, pz,
+                                             b, fullgrad, lane);
+        if (GRAD) {
+          out[lane] = r.dk[0];
+          out[32 + lane] = r.dk[1];
+          out[64 + lane] = r.dk[2];
+        } else if (MODE == 2) {
+          out[lane] = lane < 27 ? r.dot : (lane < 30 ? r.tau[lane - 27] : 0.f);
+        } else {
+          out[lane] = r.k;
+        }
+      }
+    }
   }
 }
 
@@ -135,17 +142,19 @@ int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float*
                     int64_t m, int mode, int approx_kernel_grad, float* e, void* stream) {
   if (!svh || !feat || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH || feat->channels < 1) return NKSR_E_INVALID;
   if (m == 0) return NKSR_OK;
-  int64_t warps = m * svh->depth;
-  int grid = grid_for(warps, kWarpsPerBlock);
-  if (mode == 0)
-    k_build_rows<0><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m, false, e);
-  else if (mode == 1)
-    k_build_rows<1><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m,
-                                                                          !approx_kernel_grad, e);
-  else if (mode == 2 && approx_kernel_grad)
-    k_build_rows<2><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, xyz, base, m, false, e);
-  else
-    return NKSR_E_INVALID;
+  const int grid = grid_for(m, kWarpsPerBlock);
+  cudaStream_t s = as_stream(stream);
+  if (mode < 0 || mode > 2 || (mode == 2 && !approx_kernel_grad)) return NKSR_E_INVALID;
+  const bool full = mode == 1 && !approx_kernel_grad;
+#define NKSR_ROWS(MODE, MAXL) \
+  k_build_rows<MODE, MAXL><<<grid, kWarpsPerBlock * 32, 0, s>>>(*svh, *feat, xyz, base, m, full, e)
+  if (svh->depth <= 4) {
+    if (mode == 0) NKSR_ROWS(0, 4); else if (mode == 1) NKSR_ROWS(1, 4); else NKSR_ROWS(2, 4);
+  } else {
+    if (mode == 0) NKSR_ROWS(0, NKSR_MAX_DEPTH); else if (mode == 1) NKSR_ROWS(1, NKSR_MAX_DEPTH);
+    else NKSR_ROWS(2, NKSR_MAX_DEPTH);
+  }
+#undef NKSR_ROWS
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

@@ -74,7 +74,12 @@ def reconstruct_distributed(reconstructor, xyz: torch.Tensor, normal: Optional[t
     cidx = torch.floor(xyz / chunk_size).long()
     cores, counts = torch.unique(cidx, dim=0, return_counts=True)
     owner = assign_chunks(counts.tolist(), world)
+    from .meshing import DualMesh
     from .reconstructor import DEFAULT_VOXEL_SIZE
+    if rank not in owner:                        # more ranks than chunks: contribute an empty piece
+        v, f = gather_mesh(torch.zeros((0, 3), device=xyz.device),
+                           torch.zeros((0, 3), dtype=torch.int64, device=xyz.device), 0, group)
+        return None, (None if v is None else DualMesh(v=v, f=f, c=None))
     field = reconstructor._reconstruct_chunks(
         xyz, normal, sensor, DEFAULT_VOXEL_SIZE, float(chunk_size), preprocess_fn,
         solver_kwargs.get("approx_kernel_grad", False), solver_kwargs.get("solver_tol", 1e-5),

@@ -58,9 +58,10 @@ class BaseField:
             self.mask_field.to_(device)
         return self
 
-    def extract_dual_mesh(self, grid_upsample: int = 1, mise_iter: int = 0, max_points: int = -1):
+    def extract_dual_mesh(self, grid_upsample: int = 1, mise_iter: int = 0, max_points: int = -1, cell_filter=None):
         from .meshing import extract_dual_mesh
-        return extract_dual_mesh(self, grid_upsample=grid_upsample, mise_iter=mise_iter, max_points=max_points)
+        return extract_dual_mesh(self, grid_upsample=grid_upsample, mise_iter=mise_iter, max_points=max_points,
+                                 cell_filter=cell_filter)
 
 
 def _as_level_list(features, depth):
@@ -150,6 +151,31 @@ class KernelField(BaseField):
     def solve(self, pos_xyz, normal_xyz=None, normal_value=None, pos_weight=1.0, normal_weight=1.0,
               reg_weight=1.0, fused_mode: bool = False):
         """Assemble A = E^T W E + reg R (CSR) and solve A alpha = E^T W t with Jacobi-PCG."""
+        sysm = self.assemble(pos_xyz, normal_xyz, normal_value, pos_weight, normal_weight, reg_weight)
+        dev, n = self.svh.device, sysm.n
+        tm = getattr(self, "_timer", None) or _lib.StageTimer(dev, enabled=False)
+        alpha = torch.empty(n, dtype=torch.float32, device=dev)
+        nb = call("nksr_pcg_workspace_bytes", n)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        info = (C.c_double * 4)()
+        profile = int(bool(self.solver_config.get("profile")))
+        call("nksr_pcg_solve", sysm.rowptr, sysm.col, sysm.val, sysm.diag, sysm.rhs, alpha, n,
+             float(self.solver_config["tol"]), int(self.solver_config["max_iter"]),
+             int(self.solver_config["check_every"]), profile, ws, nb, info, stream_ptr(dev))
+        tm.mark("pcg")
+        self.alpha = alpha
+        self.solve_info = {"iterations": int(info[0]), "relative_residual": float(info[1]), "n": n, "nnz": sysm.nnz}
+        if profile:
+            self.solve_info.update(spmv_ms=float(info[2]), spmv_launches=int(info[3]))
+        if self.solver_config.get("verbose"):
+            print(f"[nksr_b200] PCG: n={n} nnz={sysm.nnz} iters={int(info[0])} relres={float(info[1]):.3e}")
+        if self.solver_config.get("keep_system"):
+            self.system = sysm
+        return self
+
+    def assemble(self, pos_xyz, normal_xyz=None, normal_value=None, pos_weight=1.0, normal_weight=1.0,
+                 reg_weight=1.0):
+        """Kernel rows + Gram assembly: returns the CSR system (rowptr, col, val, rhs, diag, n, nnz)."""
         svh = self.svh
         dev = svh.device
         _lib.require_cuda(pos_xyz, "pos_xyz")
@@ -214,24 +240,8 @@ class KernelField(BaseField):
                     call("nksr_gram_sort_down", cnt, cnt_down, rowptr, rows, rows.numel(), cap, col, val, st)
         del keep
         tm.mark("gram_sort")
-        alpha = torch.empty(n, dtype=torch.float32, device=dev)
-        nb = call("nksr_pcg_workspace_bytes", n)
-        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-        info = (C.c_double * 4)()
-        profile = int(bool(self.solver_config.get("profile")))
-        call("nksr_pcg_solve", rowptr, col, val, diag, rhs, alpha, n, float(self.solver_config["tol"]),
-             int(self.solver_config["max_iter"]), int(self.solver_config["check_every"]), profile, ws, nb, info, st)
-        tm.mark("pcg")
-        self.alpha = alpha
-        self.solve_info = {"iterations": int(info[0]), "relative_residual": float(info[1]), "n": n, "nnz": nnz}
-        if profile:
-            self.solve_info.update(spmv_ms=float(info[2]), spmv_launches=int(info[3]))
-        if self.solver_config.get("verbose"):
-            print(f"[nksr_b200] PCG: n={n} nnz={nnz} iters={int(info[0])} relres={float(info[1]):.3e}")
-        if self.solver_config.get("keep_system"):
-            self.system = SimpleNamespace(rowptr=rowptr, col=col, val=val, rhs=rhs, diag=diag, cnt=cnt,
-                                          cnt_down=cnt_down)
-        return self
+        return SimpleNamespace(rowptr=rowptr, col=col, val=val, rhs=rhs, diag=diag, cnt=cnt, cnt_down=cnt_down,
+                               n=n, nnz=nnz)
 
     # the reference exposes both spellings; both run the same fused assembly here
     def solve_non_fused(self, pos_xyz, normal_xyz, normal_value, pos_weight, normal_weight, reg_weight):

@@ -31,7 +31,10 @@ def _evaluate(field, xyz, max_points):
     return out
 
 
-def extract_dual_mesh(field, grid_upsample: int = 1, mise_iter: int = 0, max_points: int = -1) -> DualMesh:
+def extract_dual_mesh(field, grid_upsample: int = 1, mise_iter: int = 0, max_points: int = -1,
+                      cell_filter=None) -> DualMesh:
+    """`cell_filter` (optional, (n_0,) bool): only dual cells whose min-corner voxel passes are meshed --
+    used by the multi-GPU path so that every rank meshes the cells it owns."""
     svh = field.svh
     dev = svh.device
     st = stream_ptr(dev)
@@ -48,6 +51,8 @@ def extract_dual_mesh(field, grid_upsample: int = 1, mise_iter: int = 0, max_poi
     # ---- stage-0 cells: duals of 2x2x2 active finest voxels
     flag = torch.empty(n0, dtype=torch.int32, device=dev)
     call("nksr_mesh_cell_flags", svh.view(), flag, st)
+    if cell_filter is not None:
+        flag = (flag * cell_filter.to(torch.int32)).contiguous()
     scan = _lib.exclusive_scan32(flag)
     n_cells = int(scan[-1].item())
     if n_cells == 0:

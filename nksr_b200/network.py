@@ -66,6 +66,7 @@ class NKSRNetwork(nn.Module):
         self.tree_depth = int(hp["tree_depth"])
         self.adaptive_depth = int(hp["adaptive_depth"])
         self.feature = hp["feature"]
+        self.compute_structure = False
         interp = hp["interpolator"]
         gen = torch.Generator().manual_seed(int(hp["seed"]))
         state = torch.random.get_rng_state()
@@ -127,7 +128,8 @@ class NKSRNetwork(nn.Module):
             x = torch.cat([nrm, torch.log1p(cnt)], dim=1)
             basis[l] = (1.0 + 0.1 * torch.tanh(self.basis_heads[l](x))) / (C ** 0.5)
             normal[l] = nrm
-            structure[l] = self.structure_heads[l](x)
+            if self.compute_structure:          # only the training losses read it (models/loss.py:152)
+                structure[l] = self.structure_heads[l](x)
             udf[l] = basis[l]
         out = FeatureBundle(basis_features=basis, normal_features=normal, structure_features=structure,
                             udf_features=udf)

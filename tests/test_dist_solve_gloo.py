@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests (CPU tensors) of the global-solve host logic in nksr_b200/dist_solve.py:
+slab bounds, ownership, the (level, key) halo join and the neighbour exchange."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nksr_b200 import dist_solve as ds
+    try:
+        # two levels; "keys" double as coordinates: level-0 key k sits at x = k + 0.5, level-1 at 2k + 1
+        bounds = [-float("inf"), 50.0, float("inf")]
+        lo0, hi0 = (0, 60) if rank == 0 else (40, 100)                 # local = slab + halo of 10
+        keys0 = torch.arange(lo0, hi0, dtype=torch.int64)
+        keys1 = torch.arange(lo0 // 2, hi0 // 2, dtype=torch.int64)
+        owner = [ds.owner_of(keys0.double() + 0.5, bounds), ds.owner_of(keys1.double() * 2 + 1.0, bounds)]
+        offsets = [0, keys0.numel()]
+        plan = ds.build_halo_plan([keys0, keys1], owner, offsets)
+        owned = torch.cat([o == rank for o in owner])
+        # every unknown carries a rank-independent global value; halo entries start poisoned
+        truth = torch.cat([keys0.float() * 3.0, 1000.0 + keys1.float() * 7.0])
+        vec = torch.where(owned, truth, torch.full_like(truth, -1.0))
+        plan.exchange(vec)
+        assert torch.equal(vec, truth), (rank, (vec != truth).nonzero().reshape(-1)[:5])
+        assert sum(i.numel() for i in plan.recv_idx) == int((~owned).sum())
+        # global dot product over owned entries = dot over the union exactly once
+        s = ds._gsum(truth.double() * owned, None)
+        ref = (torch.arange(0, 100).double() * 3.0).sum() + (1000.0 + torch.arange(0, 50).double() * 7.0).sum()
+        assert abs(float(s) - float(ref)) < 1e-9
+        # slab bounds: increasing, snapped to the quantum, same on every rank
+        coord = torch.linspace(-3.0, 17.0, 10001)
+        b = ds.slab_bounds(coord, 4, 0.8)
+        assert len(b) == 5 and all(b[i] < b[i + 1] for i in range(4))
+        assert all(abs(v / 0.8 - round(v / 0.8)) < 1e-9 for v in b[1:-1])
+        got = [None] * world
+        dist.all_gather_object(got, b)
+        assert got[0] == got[1]
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()[-400:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_join_and_exchange_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res

@@ -308,3 +308,16 @@ def test_neural_field_mask_and_texture(cuda):
     # evaluate_f_bar: masked-out side reads as outside
     fb = field.evaluate_f_bar(t(np.array([[0.33, 0.0, 0.0], [-0.33, 0.0, 0.0]], np.float32)))
     assert fb[0] <= 0 and fb[1] > 0, fb
+
+
+def test_reconstruct_distributed_single_rank(cuda):
+    """dist.reconstruct_distributed without an initialised process group = all chunks on this rank."""
+    import nksr_b200
+    from nksr_b200 import dist as nd
+    xyz, nrm = clouds.sphere(40000, radius=3.5, noise=0.01)
+    rec = nksr_b200.Reconstructor(cuda)
+    field, mesh = nd.reconstruct_distributed(rec, torch.from_numpy(xyz).to(cuda), torch.from_numpy(nrm).to(cuda),
+                                              chunk_size=4.0, mise_iter=0)
+    r = np.linalg.norm(_np(mesh.v), axis=1)
+    assert mesh.f.shape[0] > 500 and abs(np.median(r) - 3.5) < 0.05
+    assert len(field.fields) == 8            # 2 x 2 x 2 chunks of edge 4 around the origin
