@@ -94,6 +94,9 @@ NKSR_API int nksr_locate(const nksr_svh_t* svh, const float* xyz, int64_t m, int
  * the encoder stand-in that feeds models/nksr_net.py:73-78) */
 NKSR_API int nksr_pool27(const int32_t* nbr27, const float* in, int64_t n, int channels, float* out,
                 void* stream);
+/* out[p][c] = sum of in[child][c] over the children of voxel p (n = voxels of the parent level) */
+NKSR_API int nksr_pool_children(const int32_t* child8, const float* in, int64_t n, int channels,
+                       float* out, void* stream);
 /* first/last+1 sorted location of every level-l voxel: range[2*u], range[2*u+1] */
 NKSR_API int nksr_row_ranges(const int32_t* base_l, int64_t m, int32_t* range, int64_t n_l, void* stream);
 
@@ -124,7 +127,18 @@ typedef struct {
   float w_nrm;
   float w_reg;
   int32_t nrm_compact;       /* 1: e_nrm holds compact rows [K][L][32] (nksr_build_rows mode 2) */
+  /* per-voxel Gram blocks of the coarse levels l >= split_level (nksr_gram_blocks); NULL = none.
+   * Block of (level l, voxel u, offset k) starts at (mblock_off[l] + u*(depth-l) + k) * 28*32 floats */
+  const float* mblocks;
+  int32_t split_level;
+  int64_t mblock_off[NKSR_MAX_DEPTH];
 } nksr_constraints_t;
+/* floats needed for the blocks of levels >= split_level */
+NKSR_API int64_t nksr_gram_block_floats(const nksr_svh_t* svh, int split_level);
+/* reduce, once per coarse voxel, the 27x27 products of its constraint rows (c->mblock_off and
+ * c->split_level must be set; c->mblocks is ignored here) */
+NKSR_API int nksr_gram_blocks(const nksr_svh_t* svh, const nksr_constraints_t* c, float* mblocks,
+                     void* stream);
 /* numeric assembly: fills col/val (CSR, int64 rowptr), rhs b, diag. cursor[n] must be zero. */
 NKSR_API int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c,
                    const int32_t* cnt, const int64_t* rowptr, int32_t* col, float* val,

@@ -33,7 +33,8 @@ class FeatT(C.Structure):
 class ConstraintsT(C.Structure):
     _fields_ = [("e_pos", C.c_void_p), ("range_pos", C.c_void_p), ("n_pos", C.c_int64), ("w_pos", C.c_float),
                 ("e_nrm", C.c_void_p), ("range_nrm", C.c_void_p), ("t_nrm", C.c_void_p), ("n_nrm", C.c_int64),
-                ("w_nrm", C.c_float), ("w_reg", C.c_float), ("nrm_compact", C.c_int32)]
+                ("w_nrm", C.c_float), ("w_reg", C.c_float), ("nrm_compact", C.c_int32),
+                ("mblocks", C.c_void_p), ("split_level", C.c_int32), ("mblock_off", C.c_int64 * MAX_DEPTH)]
 
 
 _T = {"p": C.c_void_p, "q": C.c_int64, "i": C.c_int32, "f": C.c_float, "z": C.c_size_t,
@@ -58,11 +59,14 @@ _SIGNATURES = {
     "nksr_locate": ("i", "Spqpp"),
     "nksr_row_ranges": ("i", "pqpqp"),
     "nksr_pool27": ("i", "ppqipp"),
+    "nksr_pool_children": ("i", "ppqipp"),
     "nksr_build_rows": ("i", "SFppqiipp"),
     "nksr_gram_count": ("i", "Sppp"),
     "nksr_scan_workspace_bytes": ("z", "q"),
     "nksr_gram_rowptr": ("i", "ppqppzp"),
     "nksr_gram_fill": ("i", "SFKppppppp" + "p"),
+    "nksr_gram_block_floats": ("q", "Si"),
+    "nksr_gram_blocks": ("i", "SKpp"),
     "nksr_gram_sort_down": ("i", "ppppqippp"),
     "nksr_nbr125_search": ("i", "pqpp"),
     "nksr_spmv": ("i", "pppppqp"),
@@ -111,7 +115,7 @@ def load():
     lib = C.CDLL(path)
     for name, (ret, args) in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
-        fn.restype = {"i": C.c_int, "z": C.c_size_t, "s": C.c_char_p}[ret]
+        fn.restype = {"i": C.c_int, "z": C.c_size_t, "s": C.c_char_p, "q": C.c_int64}[ret]
         fn.argtypes = [_T[a] for a in args]
     _lib = lib
     return lib

@@ -24,6 +24,7 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kMaxSlots = 125 + 64 * (NKSR_MAX_DEPTH - 1);
+constexpr int kBlockFloats = 28 * NKSR_ROW_STRIDE;  // one per-voxel Gram block (see k_gram_blocks)
 
 __constant__ signed char c_d27[27][3] = {
     {-1, -1, -1}, {-1, -1, 0}, {-1, -1, 1}, {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {-1, 1, -1}, {-1, 1, 0}, {-1, 1, 1},
@@ -121,6 +122,60 @@ __global__ void k_set_last(const int32_t* cnt, const int32_t* cnt_down, int64_t 
   if (threadIdx.x == 0 && blockIdx.x == 0) rowptr[n] = rowptr[n - 1] + cnt[n - 1] + cnt_down[n - 1];
 }
 
+// Per-voxel Gram blocks for the COARSE levels (l >= split_level), where a voxel owns hundreds to
+// thousands of constraint rows: one warp per (voxel u, level offset k) reduces
+//   M[si][s] = sum_rows w * E_l[row][si] * E_{l+k}[row][s]      (27 x 27, lane s keeps column s)
+// ONCE, instead of each of the 27 matrix rows around u streaming all of u's constraint rows again.
+// Block layout: 28 lines of 32 floats -- lines 0..26 = M[si][:], line 27 = rhs share per si (k = 0).
+template <int MAXL>
+__global__ void __launch_bounds__(kWarps * 32)
+k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks) {
+  const int lane = threadIdx.x & 31;
+  int64_t w = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  int l = cs.split_level;
+  while (l < svh.depth && w >= svh.n[l] * (svh.depth - l)) { w -= svh.n[l] * (svh.depth - l); ++l; }
+  if (l >= svh.depth) return;
+  const int L = svh.depth;
+  const int nlev = L - l;
+  const int u = (int)(w / nlev), k = (int)(w - (int64_t)u * nlev);
+  float m[27];
+#pragma unroll
+  for (int s = 0; s < 27; ++s) m[s] = 0.f;
+  float bvec = 0.f;
+  if (cs.range_pos) {
+    const int32_t* rp = cs.range_pos + 2 * (svh.offset[l] + u);
+    const int pb = __ldg(rp), pe = __ldg(rp + 1);
+    for (int q = pb; q < pe; ++q) {
+      const float* p0 = cs.e_pos + ((int64_t)q * L + l) * NKSR_ROW_STRIDE + lane;
+      const float e0 = __ldg(p0);
+      const float el = cs.w_pos * e0;
+      const float ek = k == 0 ? e0 : __ldg(p0 + k * NKSR_ROW_STRIDE);
+#pragma unroll
+      for (int s = 0; s < 27; ++s) m[s] = fmaf(__shfl_sync(0xffffffffu, el, s), ek, m[s]);
+    }
+  }
+  if (cs.range_nrm) {
+    const int32_t* rn = cs.range_nrm + 2 * (svh.offset[l] + u);
+    const int nb = __ldg(rn), ne = __ldg(rn + 1);
+    for (int q = nb; q < ne; ++q) {
+      const float* p0 = cs.e_nrm + ((int64_t)q * L + l) * (3 * NKSR_ROW_STRIDE) + lane;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        const float e0 = __ldg(p0 + ax * NKSR_ROW_STRIDE);
+        const float el = cs.w_nrm * e0;
+        const float ek = k == 0 ? e0 : __ldg(p0 + (k * 3 + ax) * NKSR_ROW_STRIDE);
+        if (k == 0) bvec = fmaf(el, __ldg(cs.t_nrm + (int64_t)q * 3 + ax), bvec);
+#pragma unroll
+        for (int s = 0; s < 27; ++s) m[s] = fmaf(__shfl_sync(0xffffffffu, el, s), ek, m[s]);
+      }
+    }
+  }
+  float* blk = mblocks + (cs.mblock_off[l] + (int64_t)u * nlev + k) * kBlockFloats;
+#pragma unroll
+  for (int s = 0; s < 27; ++s) blk[s * NKSR_ROW_STRIDE + lane] = m[s];
+  blk[27 * NKSR_ROW_STRIDE + lane] = bvec;
+}
+
 template <bool COMPACT, int MAXL>
 __global__ void __launch_bounds__(kWarps * 32, MAXL <= 4 ? 4 : 2)
 k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_total,
@@ -166,6 +221,7 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
   constexpr int pos_level = NKSR_ROW_STRIDE;
   constexpr int nrm_level = NKSR_ROW_STRIDE * (COMPACT ? 1 : 3);
   (void)N; (void)K;
+  const bool use_blocks = cs.mblocks != nullptr && l >= cs.split_level;
   __syncwarp();
 
   for (int us = 0; us < 27; ++us) {
@@ -178,6 +234,15 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
     float r[MAXL];
 #pragma unroll
     for (int k = 0; k < MAXL; ++k) r[k] = 0.f;
+    if (use_blocks) {
+      // coarse level: the 27 x 27 products of u's constraint rows were reduced once per voxel by
+      // k_gram_blocks; this row only picks its line of every block (and its share of the rhs)
+      const float* blk = cs.mblocks + (cs.mblock_off[l] + (int64_t)u * (nup + 1)) * kBlockFloats;
+      bsum += __ldg(blk + 27 * NKSR_ROW_STRIDE + si);
+#pragma unroll
+      for (int k = 0; k < MAXL; ++k)
+        if (k <= nup) r[k] = __ldg(blk + (int64_t)k * kBlockFloats + si * NKSR_ROW_STRIDE + lane);
+    } else {
     for (int q = pb; q < pe; ++q) {
       const float* p0 = cs.e_pos + ((int64_t)q * L + l) * NKSR_ROW_STRIDE;
       const float a = cs.w_pos * __ldg(p0 + si);
@@ -231,6 +296,7 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
         }
       }
     }
+    }  // !use_blocks
     // flush: every lane < 27 owns a distinct structural slot per level
     if (lane < 27) {
       const int udx = c_d27[us][0], udy = c_d27[us][1], udz = c_d27[us][2];
@@ -390,6 +456,28 @@ int nksr_gram_rowptr(const int32_t* cnt, const int32_t* cnt_down, int64_t n, int
   if (need > ws_bytes) return NKSR_E_WORKSPACE;
   if (cub::DeviceScan::ExclusiveSum(ws, need, it, rowptr, n, as_stream(stream)) != cudaSuccess) return NKSR_E_CUDA;
   k_set_last<<<1, 32, 0, as_stream(stream)>>>(cnt, cnt_down, n, rowptr);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int64_t nksr_gram_block_floats(const nksr_svh_t* svh, int split_level) {
+  if (!svh || split_level < 0) return 0;
+  int64_t blocks = 0;
+  for (int l = split_level; l < svh->depth; ++l) blocks += svh->n[l] * (svh->depth - l);
+  return blocks * kBlockFloats;
+}
+
+int nksr_gram_blocks(const nksr_svh_t* svh, const nksr_constraints_t* c, float* mblocks, void* stream) {
+  if (!svh || !c || !mblocks || c->nrm_compact || c->split_level < 0 || c->split_level > svh->depth)
+    return NKSR_E_INVALID;
+  int64_t warps = 0;
+  for (int l = c->split_level; l < svh->depth; ++l) warps += svh->n[l] * (svh->depth - l);
+  if (warps == 0) return NKSR_OK;
+  const int grid = grid_for(warps, kWarps);
+  if (svh->depth <= 4)
+    k_gram_blocks<4><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
+  else
+    k_gram_blocks<NKSR_MAX_DEPTH><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

@@ -165,6 +165,22 @@ __global__ void k_pool27(const int32_t* __restrict__ nbr27, const float* __restr
   }
 }
 
+// out[p][c] = sum over the (<= 8) children of voxel p of in[child][c]
+__global__ void k_pool_children(const int32_t* __restrict__ child8, const float* __restrict__ in, int64_t n,
+                                int channels, float* __restrict__ out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n * channels) return;
+  const int64_t p = t / channels;
+  const int c = (int)(t - p * channels);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = __ldg(child8 + p * 8 + j);
+    if (ch >= 0) s += __ldg(in + (int64_t)ch * channels + c);
+  }
+  out[t] = s;
+}
+
 __global__ void k_row_ranges(const int32_t* __restrict__ base, int64_t m, int32_t* __restrict__ range) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -326,6 +342,14 @@ int nksr_pool27(const int32_t* nbr27, const float* in, int64_t n, int channels, 
   if (channels < 1) return NKSR_E_INVALID;
   if (n == 0) return NKSR_OK;
   k_pool27<<<grid_for(n, 8), 256, 0, as_stream(stream)>>>(nbr27, in, n, channels, out);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_pool_children(const int32_t* child8, const float* in, int64_t n, int channels, float* out, void* stream) {
+  if (channels < 1) return NKSR_E_INVALID;
+  if (n == 0) return NKSR_OK;
+  k_pool_children<<<grid_for(n * channels, 256), 256, 0, as_stream(stream)>>>(child8, in, n, channels, out);
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

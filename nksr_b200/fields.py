@@ -225,6 +225,23 @@ class KernelField(BaseField):
         rhs = torch.empty(n, dtype=torch.float32, device=dev)
         diag = torch.zeros(n, dtype=torch.float32, device=dev)
         cursor = torch.zeros(n, dtype=torch.int32, device=dev)
+        # coarse levels (>= split): a voxel owns hundreds of constraint rows, so their 27x27 products
+        # are reduced once per voxel (nksr_gram_blocks) and the matrix rows only gather block lines
+        cs.mblocks, cs.split_level = None, svh.depth
+        split = int(self.solver_config.get("block_split_level", 2))
+        if split < svh.depth and not cs.nrm_compact:
+            nfl = call("nksr_gram_block_floats", svh.view(), split)
+            if 0 < nfl * 4 <= 24e9:
+                off = 0
+                for l in range(split, svh.depth):
+                    cs.mblock_off[l] = off
+                    off += svh.num_voxels(l) * (svh.depth - l)
+                cs.split_level = split
+                mblocks = torch.empty(nfl, dtype=torch.float32, device=dev)
+                call("nksr_gram_blocks", svh.view(), cs, mblocks, st)
+                cs.mblocks = mblocks.data_ptr()
+                keep.append(mblocks)
+                tm.mark("gram_blocks")
         call("nksr_gram_fill", svh.view(), self.feat_view(), cs, cnt, rowptr, col, val, rhs, diag, cursor, st)
         tm.mark("gram_fill")
         # deterministic storage order of the transposed (finer-level) segments

@@ -101,9 +101,9 @@ class NKSRNetwork(nn.Module):
                 ok = base0 >= 0
                 acc.index_add_(0, base0[ok], src[ok])
             else:                                                       # sum of the (<= 8) children
-                ch = svh.child8[l].long()
-                acc = torch.where((ch >= 0)[:, :, None], acc[ch.clamp(min=0)],
-                                  torch.zeros((), device=xyz.device)).sum(dim=1).contiguous()
+                up = torch.empty((n, 4), device=xyz.device)
+                call("nksr_pool_children", svh.child8[l], acc, n, 4, up, stream_ptr(xyz.device))
+                acc = up
             # smooth over the 27-neighbourhood so that splat-only voxels receive a value
             out = torch.empty_like(acc)
             call("nksr_pool27", svh.nbr27[l], acc, n, 4, out, stream_ptr(xyz.device))

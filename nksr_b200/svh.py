@@ -105,9 +105,12 @@ class SparseFeatureHierarchy:
             call("nksr_child_table", allk[l], self.parent[l], n, self.child8[l + 1], nu, st)
         self.nbr27[L] = torch.empty((self.top_keys.numel(), 27), dtype=torch.int32, device=dev)
         call("nksr_nbr27_search", self.top_keys, self.top_keys.numel(), self.nbr27[L], st)
-        top = self.keys[L - 1]
-        self.nbr125_top = torch.empty((top.numel(), 125), dtype=torch.int32, device=dev)
-        call("nksr_nbr125_search", top, top.numel(), self.nbr125_top, st)
+        if L >= _lib.MAX_DEPTH:        # no room for the virtual level in the C view: explicit 5^3 table instead
+            top = self.keys[L - 1]
+            self.nbr125_top = torch.empty((top.numel(), 125), dtype=torch.int32, device=dev)
+            call("nksr_nbr125_search", top, top.numel(), self.nbr125_top, st)
+        else:
+            self.nbr125_top = None
         for l in range(L - 1, -1, -1):
             n = self.keys[l].numel()
             self.nbr27[l] = torch.empty((n, 27), dtype=torch.int32, device=dev)
