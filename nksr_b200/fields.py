@@ -220,18 +220,22 @@ class KernelField(BaseField):
         call("nksr_gram_rowptr", cnt, cnt_down, n, rowptr, ws, nb, st)
         nnz = int(rowptr[-1].item())
         tm.mark("gram_count")
-        col = torch.empty(nnz, dtype=torch.int32, device=dev)
-        val = torch.empty(nnz, dtype=torch.float32, device=dev)
-        rhs = torch.empty(n, dtype=torch.float32, device=dev)
-        diag = torch.zeros(n, dtype=torch.float32, device=dev)
-        cursor = torch.zeros(n, dtype=torch.int32, device=dev)
         # coarse levels (>= split): a voxel owns hundreds of constraint rows, so their 27x27 products
         # are reduced once per voxel (nksr_gram_blocks) and the matrix rows only gather block lines
         cs.mblocks, cs.split_level = None, svh.depth
-        split = int(self.solver_config.get("block_split_level", 2))
+        split = self.solver_config.get("block_split_level", None)
+        free_bytes = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+        budget = free_bytes - 1.25 * (8.0 * nnz + 64.0 * n)          # leave room for the CSR arrays + PCG vectors
+        if split is None:                                            # deepest split whose blocks fit the budget
+            split = svh.depth
+            for cand in (1, 2, 3):
+                if cand < svh.depth and 4 * call("nksr_gram_block_floats", svh.view(), cand) <= min(budget, 64e9):
+                    split = cand
+                    break
+        split = int(split)
         if split < svh.depth and not cs.nrm_compact:
             nfl = call("nksr_gram_block_floats", svh.view(), split)
-            if 0 < nfl * 4 <= 24e9:
+            if 0 < nfl * 4 <= max(budget, 0):
                 off = 0
                 for l in range(split, svh.depth):
                     cs.mblock_off[l] = off
@@ -242,6 +246,11 @@ class KernelField(BaseField):
                 cs.mblocks = mblocks.data_ptr()
                 keep.append(mblocks)
                 tm.mark("gram_blocks")
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz, dtype=torch.float32, device=dev)
+        rhs = torch.empty(n, dtype=torch.float32, device=dev)
+        diag = torch.zeros(n, dtype=torch.float32, device=dev)
+        cursor = torch.zeros(n, dtype=torch.int32, device=dev)
         call("nksr_gram_fill", svh.view(), self.feat_view(), cs, cnt, rowptr, col, val, rhs, diag, cursor, st)
         tm.mark("gram_fill")
         # deterministic storage order of the transposed (finer-level) segments
