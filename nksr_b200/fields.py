@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 from types import SimpleNamespace
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
 
@@ -228,8 +228,9 @@ class KernelField(BaseField):
         budget = free_bytes - 1.25 * (8.0 * nnz + 64.0 * n)          # leave room for the CSR arrays + PCG vectors
         if split is None:                                            # deepest split whose blocks fit the budget
             split = svh.depth
-            for cand in (1, 2, 3):
-                if cand < svh.depth and 4 * call("nksr_gram_block_floats", svh.view(), cand) <= min(budget, 64e9):
+            # (level 1 was measured too: +45 GB of blocks for 4 % -- not worth it; `block_split_level` overrides)
+            for cand in (2, 3):
+                if cand < svh.depth and 4 * call("nksr_gram_block_floats", svh.view(), cand) <= min(budget, 32e9):
                     split = cand
                     break
         split = int(split)

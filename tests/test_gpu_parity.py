@@ -111,10 +111,12 @@ def _gpu_csr(field):
     return sp.csr_matrix((_np(s.val).astype(np.float64), _np(s.col), _np(s.rowptr)), shape=(n, n))
 
 
-@pytest.mark.parametrize("C,approx,compact", [(4, False, False), (16, True, False), (4, True, True)])
-def test_gram_assembly_matches_oracle(cuda, C, approx, compact):
+@pytest.mark.parametrize("C,approx,compact,split", [(4, False, False, None), (16, True, False, 1), (4, True, True, None),
+                                                    (4, False, False, 4), (4, True, False, 3)])
+def test_gram_assembly_matches_oracle(cuda, C, approx, compact, split):
+    """split = level from which per-voxel Gram blocks are used (None: automatic, 4: never)."""
     field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda, C, approx)
-    field.solver_config.update(keep_system=True, max_iter=0, compact_rows=compact)
+    field.solver_config.update(keep_system=True, max_iter=0, compact_rows=compact, block_split_level=split)
     t = lambda a: torch.from_numpy(a).to(cuda)
     field.solve(t(xyz), t(nxyz), t(nval), pw, nw, rw)
     A_ref, b_ref, _ = O.build_system(osvh, feats, xyz, nxyz, nval, pw, nw, rw, approx)
