@@ -217,31 +217,38 @@ def cpu_baseline_subprocess(workload, sample_points, timeout_s=420):
 def cpu_baseline(workload, sample_points, cores, seed=4):
     """Times the CPU restatement (oracle port) on `cores` processes, each reconstructing one spatial
     crop of the same synthetic scene (crops keep the scene's local density).  Returns points/sec."""
+    return cpu_baseline_steps(workload, sample_points, cores, 1, seed)[0]
+
+
+def cpu_baseline_steps(workload, sample_points, cores, n_steps, seed=4):
+    """`n_steps` timed CPU steps over one synthetic scene and one worker pool (spawned and warmed
+    before the clock starts).  Each step = `cores` spatial crops of sample_points/cores points."""
     import multiprocessing as mp
     import numpy as np
     cfg = WORKLOADS[workload]
     xyz, sensor = make_cloud(workload, seed, 0, points=min(cfg["points"], 2_000_000))
     xyz = xyz.numpy()
     W = cfg["voxel_size"]
-    per = max(sample_points // cores, 2000)
-    # crops: nearest `per` points (in x-y) around seeded anchor points
+    per = max(sample_points // cores, 1000)
     rng = np.random.default_rng(seed)
-    jobs = []
-    for a in rng.choice(xyz.shape[0], cores, replace=False):
-        d = np.abs(xyz[:, :2] - xyz[a, :2]).max(axis=1)
-        idx = np.argpartition(d, per)[:per]
-        jobs.append((xyz[idx].copy(), None, W, 4))
-    # spawn (not fork): the parent holds torch/OpenMP threads; workers start before the clock does
-    print(f"[cpu_baseline] {cores} workers x {per} points; crops ready", file=sys.stderr, flush=True)
+    results = []
+    # spawn (not fork): the parent holds torch/OpenMP threads
     with mp.get_context("spawn").Pool(cores) as pool:
         pool.map(_noop, range(cores))
-        print("[cpu_baseline] workers warm", file=sys.stderr, flush=True)
-        t0 = time.perf_counter()
-        out = pool.map(_cpu_reconstruct_chunk, jobs)
-        wall = time.perf_counter() - t0
-    print(f"[cpu_baseline] done in {wall:.1f} s", file=sys.stderr, flush=True)
-    pts = sum(o[0] for o in out)
-    return pts / wall, pts, wall, out
+        _log(f"cpu baseline: {cores} workers warm, {per} points per crop")
+        for s in range(n_steps):
+            jobs = []
+            for a in rng.choice(xyz.shape[0], cores, replace=False):    # crops: nearest points in x-y
+                d = np.abs(xyz[:, :2] - xyz[a, :2]).max(axis=1)
+                idx = np.argpartition(d, per)[:per]
+                jobs.append((xyz[idx].copy(), None, W, 4))
+            t0 = time.perf_counter()
+            out = pool.map(_cpu_reconstruct_chunk, jobs)
+            wall = time.perf_counter() - t0
+            pts = sum(o[0] for o in out)
+            results.append((pts / wall, pts, wall, out))
+            _log(f"cpu baseline step {s}: {pts} points in {wall:.1f} s")
+    return results
 
 
 def run_reference(args):
@@ -253,11 +260,12 @@ def run_reference(args):
         os.environ.setdefault(var, "1")
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     workload = args.workload
-    vals = []
-    for s in range(args.warmup + args.steps):
-        v, pts, wall, out = cpu_baseline(workload, args.cpu_sample, cores, seed=4 + s)
-        if s >= args.warmup:
-            vals.append((v, pts, wall))
+    total = args.warmup + args.steps
+    # bounded sample: the whole run (all steps) processes about --cpu-sample * 6 points, i.e. a couple of
+    # minutes of CPU work on this path however many steps are requested
+    sample = max(min(args.cpu_sample, (6 * args.cpu_sample) // max(total, 1)), 1000 * cores)
+    res = cpu_baseline_steps(workload, sample, cores, total)
+    vals = [(v, pts, wall) for (v, pts, wall, _) in res[args.warmup:]]
     v = sum(p for _, p, _ in vals) / sum(w for _, _, w in vals)
     sample = f"{cores} spatial crops x {vals[0][1] // cores} points of {workload} per step (numpy/scipy oracle, 1 process per core)"
     line = {"impl": "reference", "metric": "points/sec reconstruct()", "value": v, "unit": "points/s",
