@@ -25,6 +25,16 @@ from ._lib import call, stream_ptr
 from .svh import SparseFeatureHierarchy
 
 
+_TOTAL_MEMORY = {}
+
+
+def _total_memory(dev) -> int:
+    key = torch.device(dev).index or 0
+    if key not in _TOTAL_MEMORY:
+        _TOTAL_MEMORY[key] = int(torch.cuda.get_device_properties(dev).total_memory * 0.94)   # driver / context reserve
+    return _TOTAL_MEMORY[key]
+
+
 class EvaluationResult(SimpleNamespace):
     """`.value` (M,) and `.gradient` (M,3) as consumed at models/loss.py:189-198."""
 
@@ -224,7 +234,8 @@ class KernelField(BaseField):
         # are reduced once per voxel (nksr_gram_blocks) and the matrix rows only gather block lines
         cs.mblocks, cs.split_level = None, svh.depth
         split = self.solver_config.get("block_split_level", None)
-        free_bytes = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+        # (allocator bookkeeping only: cudaMemGetInfo costs tens of milliseconds next to large allocations)
+        free_bytes = _total_memory(dev) - torch.cuda.memory_allocated(dev)
         budget = free_bytes - 1.25 * (8.0 * nnz + 64.0 * n)          # leave room for the CSR arrays + PCG vectors
         if split is None:                                            # deepest split whose blocks fit the budget
             split = svh.depth
