@@ -127,6 +127,19 @@ __global__ void k_set_last(const int32_t* cnt, const int32_t* cnt_down, int64_t 
 //   M[si][s] = sum_rows w * E_l[row][si] * E_{l+k}[row][s]      (27 x 27, lane s keeps column s)
 // ONCE, instead of each of the 27 matrix rows around u streaming all of u's constraint rows again.
 // Block layout: 28 lines of 32 floats -- lines 0..26 = M[si][:], line 27 = rhs share per si (k = 0).
+// m[s] += el[lane s] * ek for the 27 stencil slots s: 27 shuffles feeding 14 packed FFMA2 (sm_100)
+__device__ __forceinline__ void gram_block_update(float (&m)[28], float el, float ek) {
+  const float2 ek2 = make_float2(ek, ek);
+#pragma unroll
+  for (int s = 0; s < 28; s += 2) {
+    const float a0 = __shfl_sync(0xffffffffu, el, s);
+    const float a1 = __shfl_sync(0xffffffffu, el, s + 1);      // slot 27 is padding (zero)
+    const float2 acc = __ffma2_rn(make_float2(a0, a1), ek2, make_float2(m[s], m[s + 1]));
+    m[s] = acc.x;
+    m[s + 1] = acc.y;
+  }
+}
+
 template <int MAXL>
 __global__ void __launch_bounds__(kWarps * 32)
 k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks) {
@@ -138,9 +151,9 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
   const int L = svh.depth;
   const int nlev = L - l;
   const int u = (int)(w / nlev), k = (int)(w - (int64_t)u * nlev);
-  float m[27];
+  float m[28];
 #pragma unroll
-  for (int s = 0; s < 27; ++s) m[s] = 0.f;
+  for (int s = 0; s < 28; ++s) m[s] = 0.f;
   float bvec = 0.f;
   if (cs.range_pos) {
     const int32_t* rp = cs.range_pos + 2 * (svh.offset[l] + u);
@@ -150,8 +163,7 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
       const float e0 = __ldg(p0);
       const float el = cs.w_pos * e0;
       const float ek = k == 0 ? e0 : __ldg(p0 + k * NKSR_ROW_STRIDE);
-#pragma unroll
-      for (int s = 0; s < 27; ++s) m[s] = fmaf(__shfl_sync(0xffffffffu, el, s), ek, m[s]);
+      gram_block_update(m, el, ek);
     }
   }
   if (cs.range_nrm) {
@@ -165,8 +177,7 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
         const float el = cs.w_nrm * e0;
         const float ek = k == 0 ? e0 : __ldg(p0 + (k * 3 + ax) * NKSR_ROW_STRIDE);
         if (k == 0) bvec = fmaf(el, __ldg(cs.t_nrm + (int64_t)q * 3 + ax), bvec);
-#pragma unroll
-        for (int s = 0; s < 27; ++s) m[s] = fmaf(__shfl_sync(0xffffffffu, el, s), ek, m[s]);
+        gram_block_update(m, el, ek);
       }
     }
   }
@@ -243,13 +254,20 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
       for (int k = 0; k < MAXL; ++k)
         if (k <= nup) r[k] = __ldg(blk + (int64_t)k * kBlockFloats + si * NKSR_ROW_STRIDE + lane);
     } else {
+    // packed fp32 FMAs (FFMA2, sm_100): two levels per instruction, same IEEE result per lane
+    float2 r2[MAXL / 2];
+#pragma unroll
+    for (int k2 = 0; k2 < MAXL / 2; ++k2) r2[k2] = make_float2(0.f, 0.f);
     for (int q = pb; q < pe; ++q) {
       const float* p0 = cs.e_pos + ((int64_t)q * L + l) * NKSR_ROW_STRIDE;
       const float a = cs.w_pos * __ldg(p0 + si);
       const float* pk = p0 + lane;
 #pragma unroll
-      for (int k = 0; k < MAXL; ++k)
-        if (k <= nup) { r[k] = fmaf(a, __ldg(pk), r[k]); pk += pos_level; }
+      for (int k2 = 0; k2 < MAXL / 2; ++k2) {
+        const float l0 = 2 * k2 <= nup ? __ldg(pk + (2 * k2) * pos_level) : 0.f;
+        const float l1 = 2 * k2 + 1 <= nup ? __ldg(pk + (2 * k2 + 1) * pos_level) : 0.f;
+        r2[k2] = __ffma2_rn(make_float2(a, a), make_float2(l0, l1), r2[k2]);
+      }
     }
     if (COMPACT) {
       // one line per (location, level): <phi,z_s> in slots 0..26, tau in 27..29;
@@ -291,11 +309,16 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
           bsum = fmaf(a, __ldg(t + ax), bsum);
           const float* pk = p0 + ax * NKSR_ROW_STRIDE + lane;
 #pragma unroll
-          for (int k = 0; k < MAXL; ++k)
-            if (k <= nup) { r[k] = fmaf(a, __ldg(pk), r[k]); pk += nrm_level; }
+          for (int k2 = 0; k2 < MAXL / 2; ++k2) {
+            const float l0 = 2 * k2 <= nup ? __ldg(pk + (2 * k2) * nrm_level) : 0.f;
+            const float l1 = 2 * k2 + 1 <= nup ? __ldg(pk + (2 * k2 + 1) * nrm_level) : 0.f;
+            r2[k2] = __ffma2_rn(make_float2(a, a), make_float2(l0, l1), r2[k2]);
+          }
         }
       }
     }
+#pragma unroll
+    for (int k2 = 0; k2 < MAXL / 2; ++k2) { r[2 * k2] += r2[k2].x; r[2 * k2 + 1] += r2[k2].y; }
     }  // !use_blocks
     // flush: every lane < 27 owns a distinct structural slot per level
     if (lane < 27) {
