@@ -411,6 +411,47 @@ __global__ void k_sort_down(const int32_t* __restrict__ cnt, const int32_t* __re
   }
 }
 
+// segments of 33..512 entries: one WARP per row on its own shared-memory tile; stages are separated
+// by __syncwarp only, and eight rows share a block (8x fewer blocks than a block per row)
+template <int CAP>
+__global__ void __launch_bounds__(256)
+k_sort_down_tile(const int32_t* __restrict__ cnt, const int32_t* __restrict__ cnt_down,
+                 const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rows, int64_t n_rows,
+                 int32_t* __restrict__ col, float* __restrict__ val) {
+  __shared__ unsigned long long tile[8][CAP];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t r = blockIdx.x * (int64_t)8 + wid;
+  if (r >= n_rows) return;
+  const int64_t row = rows[r];
+  const int m = cnt_down[row];
+  if (m <= 1 || m > CAP) return;
+  unsigned long long* skey = tile[wid];
+  const int64_t p0 = rowptr[row] + cnt[row];
+  int m2 = 32;
+  while (m2 < m) m2 <<= 1;
+  for (int t = lane; t < m2; t += 32)
+    skey[t] = t < m ? (((unsigned long long)(unsigned)col[p0 + t] << 32) | __float_as_uint(val[p0 + t]))
+                    : 0xffffffffffffffffull;
+  __syncwarp();
+  const int half = m2 >> 1;
+  for (int k = 2; k <= m2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int q = lane; q < half; q += 32) {
+        const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+        const int hi = lo | j;
+        const unsigned long long a = skey[lo], b = skey[hi];
+        if ((a > b) == ((lo & k) == 0)) { skey[lo] = b; skey[hi] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  for (int t = lane; t < m; t += 32) {
+    const unsigned long long v = skey[t];
+    col[p0 + t] = (int32_t)(v >> 32);
+    val[p0 + t] = __uint_as_float((unsigned)v);
+  }
+}
+
 // segments of at most 32 entries: one warp per row, bitonic network through shuffles
 __global__ void k_sort_down_warp(const int32_t* __restrict__ cnt, const int32_t* __restrict__ cnt_down,
                                  const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rows,
@@ -539,6 +580,12 @@ int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, const int64
   if (cap <= 32) {
     k_sort_down_warp<<<grid_for(n_rows, 8), 256, 0, as_stream(stream)>>>(cnt, cnt_down, rowptr, rows, n_rows, col,
                                                                         val);
+  } else if (cap <= 128) {
+    k_sort_down_tile<128><<<grid_for(n_rows, 8), 256, 0, as_stream(stream)>>>(cnt, cnt_down, rowptr, rows, n_rows,
+                                                                             col, val);
+  } else if (cap <= 512) {
+    k_sort_down_tile<512><<<grid_for(n_rows, 8), 256, 0, as_stream(stream)>>>(cnt, cnt_down, rowptr, rows, n_rows,
+                                                                             col, val);
   } else {
     const int threads = cap >= 4096 ? 512 : (cap >= 1024 ? 256 : (cap >= 256 ? 128 : 64));
     k_sort_down<<<(unsigned)n_rows, threads, cap * 8, as_stream(stream)>>>(cnt, cnt_down, rowptr, rows, n_rows, col,
