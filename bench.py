@@ -226,22 +226,24 @@ def cpu_baseline_steps(workload, sample_points, cores, n_steps, seed=4):
     import multiprocessing as mp
     import numpy as np
     cfg = WORKLOADS[workload]
-    xyz, sensor = make_cloud(workload, seed, 0, points=min(cfg["points"], 2_000_000))
+    # the FULL workload cloud is generated so that crops have the workload's own point density
+    # (a subsampled scene would have several times more unknowns per point)
+    xyz, sensor = make_cloud(workload, seed, 0, points=cfg["points"])
     xyz = xyz.numpy()
     W = cfg["voxel_size"]
     per = max(sample_points // cores, 1000)
     rng = np.random.default_rng(seed)
     results = []
+    from scipy.spatial import cKDTree
+    tree = cKDTree(xyz[:, :2])                                          # crops = `per` nearest points in x-y
     # spawn (not fork): the parent holds torch/OpenMP threads
     with mp.get_context("spawn").Pool(cores) as pool:
         pool.map(_noop, range(cores))
         _log(f"cpu baseline: {cores} workers warm, {per} points per crop")
         for s in range(n_steps):
-            jobs = []
-            for a in rng.choice(xyz.shape[0], cores, replace=False):    # crops: nearest points in x-y
-                d = np.abs(xyz[:, :2] - xyz[a, :2]).max(axis=1)
-                idx = np.argpartition(d, per)[:per]
-                jobs.append((xyz[idx].copy(), None, W, 4))
+            anchors = rng.choice(xyz.shape[0], cores, replace=False)
+            _, nn = tree.query(xyz[anchors, :2], k=per, p=np.inf)
+            jobs = [(xyz[np.atleast_1d(idx)].copy(), None, W, 4) for idx in nn]
             t0 = time.perf_counter()
             out = pool.map(_cpu_reconstruct_chunk, jobs)
             wall = time.perf_counter() - t0
