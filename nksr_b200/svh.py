@@ -86,6 +86,29 @@ class SparseFeatureHierarchy:
                 uh = _lib.unique_sorted(uh, 3)
         return self.build_from_keys(keys[:self.depth], top_keys=keys[self.depth])
 
+    def build_adaptive_normal_variation(self, xyz: torch.Tensor, normal: torch.Tensor, tau: float = 0.2,
+                                        adaptive_depth: int = 2):
+        """Adaptive hierarchy for ground-truth decoders (models/nksr_net.py:175-179): start from the
+        splatted hierarchy; a voxel of one of the finest `adaptive_depth` levels (but not level 0)
+        whose points have consistent normals -- variation 1 - |mean normal| below `tau` -- becomes a
+        leaf and every finer voxel below it is dropped.  Coarser levels are always subdivided.
+        Training-side helper: plain torch on top of the CUDA tables (outside the hot path)."""
+        self.build_point_splatting(xyz)
+        normal = normal.detach().to(self.device, torch.float32)
+        base = self.locate(xyz.detach().to(self.device, torch.float32).contiguous()).long()
+        keys = [k.clone() for k in self.keys]
+        drop = [torch.zeros(k.numel(), dtype=torch.bool, device=self.device) for k in keys]
+        for l in range(min(adaptive_depth, self.depth) - 1, 0, -1):
+            n = keys[l].numel()
+            acc = torch.zeros((n, 4), device=self.device)
+            ok = base[l] >= 0
+            acc.index_add_(0, base[l][ok], torch.cat([normal[ok], torch.ones((int(ok.sum()), 1), device=self.device)], 1))
+            variation = 1.0 - acc[:, :3].norm(dim=1) / acc[:, 3].clamp(min=1.0)
+            leaf = (variation < tau) & (acc[:, 3] > 0) & ~drop[l]
+            stop = leaf | drop[l]                           # everything below a leaf (or a dropped voxel) goes
+            drop[l - 1] |= stop[self.parent[l - 1].long()]
+        return self.build_from_keys([k[~d] for k, d in zip(keys, drop)], top_keys=self.top_keys)
+
     def build_from_keys(self, keys, top_keys=None):
         """Adopt sorted, unique, parent-closed Morton keys per level and build the tables.
         `top_keys`: keys of the virtual level above the coarsest one (default: its parents)."""
