@@ -16,6 +16,8 @@
 // and row ranges are fetched lane-parallel once per row, row pointers advance by one add per
 // level, and with approx_kernel_grad the three gradient rows are rebuilt from ONE 128-byte
 // line (<phi,z_s> + tau) with nine FMAs instead of being loaded.
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -187,8 +189,8 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
   blk[27 * NKSR_ROW_STRIDE + lane] = bvec;
 }
 
-template <bool COMPACT, int MAXL>
-__global__ void __launch_bounds__(kWarps * 32, MAXL <= 4 ? 4 : 2)
+template <bool COMPACT, int MAXL, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB)
 k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_total,
             const int32_t* __restrict__ cnt, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col_out,
             float* __restrict__ val_out, float* __restrict__ rhs, float* __restrict__ diag,
@@ -556,12 +558,17 @@ int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_co
   cudaStream_t s = as_stream(stream);
   const size_t smem = (size_t)kWarps * kMaxSlots * sizeof(float);
   const int grid = grid_for(n, kWarps);
-#define NKSR_FILL(COMPACT, MAXL) \
-  k_gram_fill<COMPACT, MAXL><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, val, rhs, diag, cursor)
+#define NKSR_FILL(COMPACT, MAXL, MINB)                                                                          \
+  k_gram_fill<COMPACT, MAXL, MINB><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, val, rhs, \
+                                                                   diag, cursor)
+  // resident blocks per SM for the common depth <= 4 kernels: 4 (64 registers) or 5 (48 registers)
+  static const int minb = [] { const char* e = getenv("NKSR_FILL_MINB"); return e ? atoi(e) : 4; }();
   if (svh->depth <= 4) {
-    if (c->nrm_compact) NKSR_FILL(true, 4); else NKSR_FILL(false, 4);
+    if (c->nrm_compact) NKSR_FILL(true, 4, 4);
+    else if (minb == 5) NKSR_FILL(false, 4, 5);
+    else NKSR_FILL(false, 4, 4);
   } else {
-    if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH); else NKSR_FILL(false, NKSR_MAX_DEPTH);
+    if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH, 2); else NKSR_FILL(false, NKSR_MAX_DEPTH, 2);
   }
 #undef NKSR_FILL
   NKSR_CHECK_LAUNCH();

@@ -90,8 +90,8 @@ class SparseFeatureHierarchy:
                                         adaptive_depth: int = 2):
         """Adaptive hierarchy for ground-truth decoders (models/nksr_net.py:175-179): start from the
         splatted hierarchy; a voxel of one of the finest `adaptive_depth` levels (but not level 0)
-        whose points have consistent normals -- variation 1 - |mean normal| below `tau` -- becomes a
-        leaf and every finer voxel below it is dropped.  Coarser levels are always subdivided.
+        whose points have consistent normals -- variation 1 - |mean normal| below `tau` -- or that holds
+        no point at all (splat-only) becomes a leaf and every finer voxel below it is dropped.  Coarser levels are always subdivided.
         Training-side helper: plain torch on top of the CUDA tables (outside the hot path)."""
         self.build_point_splatting(xyz)
         normal = normal.detach().to(self.device, torch.float32)
@@ -104,7 +104,7 @@ class SparseFeatureHierarchy:
             ok = base[l] >= 0
             acc.index_add_(0, base[l][ok], torch.cat([normal[ok], torch.ones((int(ok.sum()), 1), device=self.device)], 1))
             variation = 1.0 - acc[:, :3].norm(dim=1) / acc[:, 3].clamp(min=1.0)
-            leaf = (variation < tau) & (acc[:, 3] > 0) & ~drop[l]
+            leaf = ((variation < tau) | (acc[:, 3] == 0)) & ~drop[l]      # point-free (splat-only) voxels are leaves too
             stop = leaf | drop[l]                           # everything below a leaf (or a dropped voxel) goes
             drop[l - 1] |= stop[self.parent[l - 1].long()]
         return self.build_from_keys([k[~d] for k, d in zip(keys, drop)], top_keys=self.top_keys)
