@@ -16,8 +16,6 @@
 // and row ranges are fetched lane-parallel once per row, row pointers advance by one add per
 // level, and with approx_kernel_grad the three gradient rows are rebuilt from ONE 128-byte
 // line (<phi,z_s> + tau) with nine FMAs instead of being loaded.
-#include <cstdlib>
-
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -561,12 +559,10 @@ int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_co
 #define NKSR_FILL(COMPACT, MAXL, MINB)                                                                          \
   k_gram_fill<COMPACT, MAXL, MINB><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, val, rhs, \
                                                                    diag, cursor)
-  // resident blocks per SM for the common depth <= 4 kernels: 4 (64 registers) or 5 (48 registers)
-  static const int minb = [] { const char* e = getenv("NKSR_FILL_MINB"); return e ? atoi(e) : 4; }();
+  // 4 resident blocks per SM (64 registers) for depth <= 4; 5 blocks (48 registers) was measured
+  // 1.7x slower (register starvation cuts the loads in flight per warp)
   if (svh->depth <= 4) {
-    if (c->nrm_compact) NKSR_FILL(true, 4, 4);
-    else if (minb == 5) NKSR_FILL(false, 4, 5);
-    else NKSR_FILL(false, 4, 4);
+    if (c->nrm_compact) NKSR_FILL(true, 4, 4); else NKSR_FILL(false, 4, 4);
   } else {
     if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH, 2); else NKSR_FILL(false, NKSR_MAX_DEPTH, 2);
   }
