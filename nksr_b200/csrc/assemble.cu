@@ -11,11 +11,14 @@
 // such row r contributes  w * E[r,i] * E[r, :]  and all rows of u share the same 27-stencils on
 // level l and on every coarser level, so lane s accumulates stencil slot s in a register and
 // the warp flushes once per u into a per-warp shared-memory tile indexed by structural slot --
-// no atomics, deterministic summation order.  The round-1 ncu capture showed the kernel to be
-// instruction-issue bound in the gradient-row loop (profiles/r1_*), hence: neighbour indices
-// and row ranges are fetched lane-parallel once per row, row pointers advance by one add per
-// level, and with approx_kernel_grad the three gradient rows are rebuilt from ONE 128-byte
-// line (<phi,z_s> + tau) with nine FMAs instead of being loaded.
+// no atomics, deterministic summation order.  The round-1 ncu captures (profiles/r1a..r1d) showed the
+// kernel to be instruction-issue / L2-latency bound, hence: neighbour indices and row ranges are
+// fetched lane-parallel once per row; constraint rows are stored location-major so every line is a
+// compile-time offset from one pointer; two levels are accumulated per packed FFMA2; 64 registers keep
+// 32 warps per SM resident; and on the coarse levels (a voxel owns hundreds of constraint rows) the
+// 27 x 27 products are reduced once per voxel by k_gram_blocks and the rows only gather block lines.
+// Optional compact gradient rows (approx_kernel_grad: one line <phi,z_s> + tau per location and level,
+// the three rows rebuilt with nine FMAs) trade 2/3 of the row memory for ALU work.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
