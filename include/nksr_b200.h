@@ -148,6 +148,25 @@ NKSR_API int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, co
                         const int32_t* rows, int64_t n_rows, int cap, int32_t* col, float* val,
                         void* stream);
 
+/* -- sort-free placement of the transposed entries (DESIGN.md SPEC S6b): same matrix, no atomics, no sort.
+ * Fine voxel j (level l) reaches coarse voxel c (level l+k) through its ancestor a = c - d; its entry sits at
+ *   rowptr[c] + cnt[c] + prefix[l][k][c*125 + slot(d)] + rank8[l][k][j*8 + S(d)],  S(d) = axes with |d| = 2. */
+typedef struct {
+  const int32_t* rank8[NKSR_MAX_DEPTH][NKSR_MAX_DEPTH];   /* [l][k] -> [n_l][8]       */
+  const int32_t* prefix[NKSR_MAX_DEPTH][NKSR_MAX_DEPTH];  /* [l][k] -> [n_{l+k}][125] */
+} nksr_placement_t;
+/* cnt[i] only (same + coarser levels); the transposed lengths come from nksr_gram_place */
+NKSR_API int nksr_gram_count_own(const nksr_svh_t* svh, int32_t* cnt, void* stream);
+/* tables of one (fine level l, offset k >= 1) pair: rank8 [n_l][8], class_count [n_{l+k}][27] (scratch),
+ * prefix [n_{l+k}][125]; advances cnt_down[offset[l+k] + c] by the entries level l adds to row c.
+ * cnt_down must start at zero and, for one coarse level, the pairs must be issued in increasing l. */
+NKSR_API int nksr_gram_place(const nksr_svh_t* svh, int l, int k, int32_t* rank8, int32_t* class_count,
+                    int32_t* prefix, int32_t* cnt_down, void* stream);
+/* nksr_gram_fill with the transposed copies written at their final position */
+NKSR_API int nksr_gram_fill_placed(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c,
+                          const int32_t* cnt, const int64_t* rowptr, const nksr_placement_t* placement,
+                          int32_t* col, float* val, float* rhs, float* diag, void* stream);
+
 /* ---- a4: PCG (solver_tol, examples/recons_waymo.py:33; verbose, models/nksr_net.py:97) ---- */
 NKSR_API int nksr_spmv(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
               float* y, int64_t n, void* stream);

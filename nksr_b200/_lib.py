@@ -37,8 +37,13 @@ class ConstraintsT(C.Structure):
                 ("mblocks", C.c_void_p), ("split_level", C.c_int32), ("mblock_off", C.c_int64 * MAX_DEPTH)]
 
 
+class PlacementT(C.Structure):
+    _fields_ = [("rank8", (C.c_void_p * MAX_DEPTH) * MAX_DEPTH), ("prefix", (C.c_void_p * MAX_DEPTH) * MAX_DEPTH)]
+
+
 _T = {"p": C.c_void_p, "q": C.c_int64, "i": C.c_int32, "f": C.c_float, "z": C.c_size_t,
-      "S": C.POINTER(SvhT), "F": C.POINTER(FeatT), "K": C.POINTER(ConstraintsT), "d": C.POINTER(C.c_double)}
+      "S": C.POINTER(SvhT), "F": C.POINTER(FeatT), "K": C.POINTER(ConstraintsT), "d": C.POINTER(C.c_double),
+      "P": C.POINTER(PlacementT)}
 
 # name -> (return kind, argument kinds); mirrors include/nksr_b200.h one to one
 _SIGNATURES = {
@@ -68,6 +73,9 @@ _SIGNATURES = {
     "nksr_gram_block_floats": ("q", "Si"),
     "nksr_gram_blocks": ("i", "SKpp"),
     "nksr_gram_sort_down": ("i", "ppppqippp"),
+    "nksr_gram_count_own": ("i", "Spp"),
+    "nksr_gram_place": ("i", "Siipppp" + "p"),
+    "nksr_gram_fill_placed": ("i", "SFKppPppppp"),
     "nksr_nbr125_search": ("i", "pqpp"),
     "nksr_spmv": ("i", "pppppqp"),
     "nksr_pcg_workspace_bytes": ("z", "q"),
@@ -132,7 +140,7 @@ def _conv(kind, v):
         if isinstance(v, torch.Tensor):
             return v.data_ptr()
         return int(v)
-    if kind in "SFK":
+    if kind in "SFKP":
         return C.byref(v)
     return v
 

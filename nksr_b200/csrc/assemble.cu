@@ -89,12 +89,45 @@ __device__ __forceinline__ int slot_column(const nksr_svh_t& svh, int l, const R
   return lookup_near(svh, l + k, a, g.ux >> k, g.uy >> k, g.uz >> k, cx, cy, cz);
 }
 
+// slot_column plus, for a coarser-level slot, where the transposed copy goes (sort-free placement):
+// ds = slot of d = c - a in c's 125-ancestor table (a = ancestor of the row voxel), sm = axes with |d| = 2
+__device__ __forceinline__ int slot_column_place(const nksr_svh_t& svh, int l, const RowGeom& g, int t, int& k_out,
+                                                 int& ds, int& sm) {
+  ds = 0;
+  sm = 0;
+  const int c = slot_column(svh, l, g, t, k_out);
+  if (t >= 125 && c >= 0) {
+    const int k = k_out, q = (t - 125) & 63;
+    const int dx = (((g.ux - 1) >> k) - 1) + (q >> 4) - (g.ux >> k);
+    const int dy = (((g.uy - 1) >> k) - 1) + ((q >> 2) & 3) - (g.uy >> k);
+    const int dz = (((g.uz - 1) >> k) - 1) + (q & 3) - (g.uz >> k);
+    ds = (dx + 2) * 25 + (dy + 2) * 5 + (dz + 2);
+    sm = ((dx == -2 || dx == 2) ? 4 : 0) | ((dy == -2 || dy == 2) ? 2 : 0) | ((dz == -2 || dz == 2) ? 1 : 0);
+  }
+  return c;
+}
+
+// kernel argument of the sort-free placement: empty for the atomic-cursor variant
+template <bool PLACED>
+struct PlaceArg {
+  __device__ __forceinline__ int pos(int, int, int64_t, int, int64_t, int) const { return 0; }
+};
+template <>
+struct PlaceArg<true> {
+  nksr_placement_t t;
+  __device__ __forceinline__ int pos(int l, int k, int64_t c, int ds, int64_t j, int sm) const {
+    return __ldg(t.prefix[l][k] + c * 125 + ds) + __ldg(t.rank8[l][k] + j * 8 + sm);
+  }
+};
+
 __device__ __forceinline__ void row_of_warp(const nksr_svh_t& svh, int64_t row, int& l, int& i) {
   l = 0;
   while (l + 1 < svh.depth && row >= svh.offset[l + 1]) ++l;
   i = (int)(row - svh.offset[l]);
 }
 
+// DOWN = false: own entries only (the transposed segments are sized by k_place_prefix)
+template <bool DOWN>
 __global__ void __launch_bounds__(kWarps * 32)
 k_gram_count(nksr_svh_t svh, int64_t n_total, int32_t* __restrict__ cnt, int32_t* __restrict__ cnt_down) {
   const int lane = threadIdx.x & 31;
@@ -109,7 +142,7 @@ k_gram_count(nksr_svh_t svh, int64_t n_total, int32_t* __restrict__ cnt, int32_t
   for (int t0 = 0; t0 < nslots; t0 += 32) {
     int t = t0 + lane, k = 0;
     int col = t < nslots ? slot_column(svh, l, g, t, k) : -1;
-    if (col >= 0 && k > 0) atomicAdd(cnt_down + svh.offset[l + k] + col, 1);
+    if (DOWN && col >= 0 && k > 0) atomicAdd(cnt_down + svh.offset[l + k] + col, 1);
     c += __popc(__ballot_sync(0xffffffffu, col >= 0));
   }
   if (lane == 0) cnt[row] = c;
@@ -123,6 +156,99 @@ struct AddPair {
 
 __global__ void k_set_last(const int32_t* cnt, const int32_t* cnt_down, int64_t n, int64_t* rowptr) {
   if (threadIdx.x == 0 && blockIdx.x == 0) rowptr[n] = rowptr[n - 1] + cnt[n - 1] + cnt_down[n - 1];
+}
+
+// ---------------------------------------------------------------- sort-free transposed placement
+// (SPEC S6b; formula checked on the CPU by oracle/placement_proto.py + tests/test_cpu_placement.py)
+// Fine voxel j (level l, coords u) stores an entry for the coarse voxel c (level l+k) iff c lies in
+// [((u-1)>>k)-1, ((u+1)>>k)+1] per axis.  With a = u>>k the ancestor of j:  c-a in {-1,0,1} always
+// qualifies, c-a = -2 needs u on the LOW edge of the ancestor block (u mod 2^k == 0) and c-a = +2 on
+// the HIGH edge.  So the fine voxels reaching c are, for each of the 125 ancestors a = c-d, the
+// descendants of a in an edge class that depends on d only, and the descendants of one ancestor are
+// contiguous in Morton order.  Ordering c's transposed segment by (level l, slot of d, Morton index j):
+//     position(j -> c) = prefix[c][slot(d)] + rank of j among the class(d) descendants of a
+// -- two small tables from prefix sums; no atomics, no sort, deterministic by construction.
+//
+// edge type per axis: 0 = interior, 1 = low edge, 2 = high edge (never both: 2^k >= 2)
+__device__ __forceinline__ int edge_type(int u, int m) { return (u & m) == 0 ? 1 : ((u & m) == m ? 2 : 0); }
+
+// One warp per ancestor a (level l+k): rank8[j*8 + S] = rank of descendant j among the descendants
+// that share j's edge types on the axes in S (S = 4*x + 2*y + z; only defined when j is on an edge
+// for every axis of S; S = 0: index of j inside the block); class_count[a*27 + cls] = members of the
+// class cls = 9*rx + 3*ry + rz, r in {0 any, 1 low, 2 high}.
+__global__ void __launch_bounds__(kWarps * 32)
+k_place_rank(nksr_svh_t svh, int l, int k, int32_t* __restrict__ rank8, int32_t* __restrict__ class_count) {
+  const int lane = threadIdx.x & 31;
+  const int lu = l + k;
+  const int64_t a = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  if (a >= svh.n[lu]) return;
+  const int64_t ka = __ldg(svh.keys[lu] + a);
+  const int64_t nl = svh.n[l];
+  const int64_t first = lower_bound_key(svh.keys[l], nl, ka << (3 * k));
+  const int64_t end = lower_bound_key(svh.keys[l], nl, (ka + 1) << (3 * k));
+  const int m = (1 << k) - 1;
+  const unsigned lt = (1u << lane) - 1u;
+  int run[27];
+#pragma unroll
+  for (int c = 0; c < 27; ++c) run[c] = 0;
+  for (int64_t j0 = first; j0 < end; j0 += 32) {
+    const int64_t j = j0 + lane;
+    const bool in = j < end;
+    int ex = 0, ey = 0, ez = 0;
+    if (in) {
+      int x, y, z;
+      morton3_decode(__ldg(svh.keys[l] + j), x, y, z);
+      ex = edge_type(x, m); ey = edge_type(y, m); ez = edge_type(z, m);
+    }
+#pragma unroll
+    for (int c = 0; c < 27; ++c) {
+      const int rx = c / 9, ry = (c / 3) % 3, rz = c % 3;
+      const bool mem = in && (rx == 0 || ex == rx) && (ry == 0 || ey == ry) && (rz == 0 || ez == rz);
+      const unsigned b = __ballot_sync(0xffffffffu, mem);
+      if (mem) rank8[j * 8 + ((rx ? 4 : 0) | (ry ? 2 : 0) | (rz ? 1 : 0))] = run[c] + __popc(b & lt);
+      run[c] += __popc(b);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 27; ++c)
+    if (lane == c) class_count[a * 27 + c] = run[c];
+}
+
+// One warp per coarse voxel c (level l+k): exclusive prefix over the 125 ancestors a = c - d (slot
+// t = (dx+2)*25 + (dy+2)*5 + (dz+2), d = c - a) of the class counts, starting at the current length of
+// c's transposed segment (the finer levels handled before); the segment length is advanced.
+__global__ void __launch_bounds__(kWarps * 32)
+k_place_prefix(nksr_svh_t svh, int l, int k, const int32_t* __restrict__ class_count,
+               int32_t* __restrict__ prefix, int32_t* __restrict__ cnt_down) {
+  const int lane = threadIdx.x & 31;
+  const int lu = l + k;
+  const int64_t c = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  if (c >= svh.n[lu]) return;
+  int cx, cy, cz;
+  morton3_decode(__ldg(svh.keys[lu] + c), cx, cy, cz);
+  int32_t* len = cnt_down + svh.offset[lu] + c;
+  int carry = *len;
+  __syncwarp();
+  for (int t0 = 0; t0 < 125; t0 += 32) {
+    const int t = t0 + lane;
+    int v = 0;
+    if (t < 125) {
+      const int dx = t / 25 - 2, dy = (t / 5) % 5 - 2, dz = t % 5 - 2;
+      const int a = lookup_near(svh, lu, (int)c, cx, cy, cz, cx - dx, cy - dy, cz - dz);
+      const int cls = (dx == -2 ? 9 : (dx == 2 ? 18 : 0)) + (dy == -2 ? 3 : (dy == 2 ? 6 : 0)) +
+                      (dz == -2 ? 1 : (dz == 2 ? 2 : 0));
+      if (a >= 0) v = __ldg(class_count + (int64_t)a * 27 + cls);
+    }
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += up;
+    }
+    if (t < 125) prefix[c * 125 + t] = carry + inc - v;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) *len = carry;
 }
 
 // Per-voxel Gram blocks for the COARSE levels (l >= split_level), where a voxel owns hundreds to
@@ -190,12 +316,12 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
   blk[27 * NKSR_ROW_STRIDE + lane] = bvec;
 }
 
-template <bool COMPACT, int MAXL, int MINB>
+template <bool COMPACT, int MAXL, int MINB, bool PLACED>
 __global__ void __launch_bounds__(kWarps * 32, MINB)
 k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_total,
             const int32_t* __restrict__ cnt, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col_out,
             float* __restrict__ val_out, float* __restrict__ rhs, float* __restrict__ diag,
-            int32_t* __restrict__ cursor) {
+            int32_t* __restrict__ cursor, const PlaceArg<PLACED> place) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
@@ -356,8 +482,9 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
   int written = 0;
   for (int t0 = 0; t0 < nslots; t0 += 32) {
     const int t = t0 + lane;
-    int k = 0;
-    const int c = t < nslots ? slot_column(svh, l, g, t, k) : -1;
+    int k = 0, ds = 0, sm = 0;
+    const int c = t >= nslots ? -1
+                              : (PLACED ? slot_column_place(svh, l, g, t, k, ds, sm) : slot_column(svh, l, g, t, k));
     const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
     if (c >= 0) {
       const int64_t p = p0 + written + __popc(m & ((1u << lane) - 1u));
@@ -367,7 +494,8 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
       val_out[p] = v;
       if (k == 0 && c == i) diag[row] = v;
       if (k > 0) {  // transposed copy into the coarse row's finer-level segment
-        const int64_t q = rowptr[gc] + cnt[gc] + atomicAdd(cursor + gc, 1);
+        const int64_t q = rowptr[gc] + cnt[gc] +
+                          (PLACED ? place.pos(l, k, c, ds, i, sm) : atomicAdd(cursor + gc, 1));
         col_out[q] = (int32_t)row;
         val_out[q] = v;
       }
@@ -498,7 +626,33 @@ int nksr_gram_count(const nksr_svh_t* svh, int32_t* cnt, int32_t* cnt_down, void
   const int64_t n = total_unknowns(svh);
   if (n == 0) return NKSR_OK;
   if (cudaMemsetAsync(cnt_down, 0, (size_t)n * sizeof(int32_t), as_stream(stream)) != cudaSuccess) return NKSR_E_CUDA;
-  k_gram_count<<<grid_for(n, kWarps), kWarps * 32, 0, as_stream(stream)>>>(*svh, n, cnt, cnt_down);
+  k_gram_count<true><<<grid_for(n, kWarps), kWarps * 32, 0, as_stream(stream)>>>(*svh, n, cnt, cnt_down);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_gram_count_own(const nksr_svh_t* svh, int32_t* cnt, void* stream) {
+  if (!svh || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
+  if (!svh->nbr125_top && !svh->parent[svh->depth - 1]) return NKSR_E_INVALID;
+  const int64_t n = total_unknowns(svh);
+  if (n == 0) return NKSR_OK;
+  k_gram_count<false><<<grid_for(n, kWarps), kWarps * 32, 0, as_stream(stream)>>>(*svh, n, cnt, nullptr);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_gram_place(const nksr_svh_t* svh, int l, int k, int32_t* rank8, int32_t* class_count, int32_t* prefix,
+                    int32_t* cnt_down, void* stream) {
+  if (!svh || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH || l < 0 || k < 1 || l + k >= svh->depth)
+    return NKSR_E_INVALID;
+  if (!svh->nbr125_top && !svh->parent[svh->depth - 1]) return NKSR_E_INVALID;
+  if (!rank8 || !class_count || !prefix || !cnt_down) return NKSR_E_INVALID;
+  const int64_t n_up = svh->n[l + k];
+  if (n_up == 0 || svh->n[l] == 0) return NKSR_OK;
+  const int grid = grid_for(n_up, kWarps);
+  k_place_rank<<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, l, k, rank8, class_count);
+  NKSR_CHECK_LAUNCH();
+  k_place_prefix<<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, l, k, class_count, prefix, cnt_down);
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }
@@ -549,9 +703,13 @@ int nksr_gram_blocks(const nksr_svh_t* svh, const nksr_constraints_t* c, float* 
   return NKSR_OK;
 }
 
-int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c, const int32_t* cnt,
-                   const int64_t* rowptr, int32_t* col, float* val, float* rhs, float* diag, int32_t* cursor,
-                   void* stream) {
+}  // extern "C"
+
+namespace {
+template <bool PLACED>
+int launch_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c, const int32_t* cnt,
+                const int64_t* rowptr, int32_t* col, float* val, float* rhs, float* diag, int32_t* cursor,
+                const PlaceArg<PLACED>& place, void* stream) {
   if (!svh || !feat || !c || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
   if (!svh->nbr125_top && !svh->parent[svh->depth - 1]) return NKSR_E_INVALID;
   const int64_t n = total_unknowns(svh);
@@ -559,9 +717,9 @@ int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_co
   cudaStream_t s = as_stream(stream);
   const size_t smem = (size_t)kWarps * kMaxSlots * sizeof(float);
   const int grid = grid_for(n, kWarps);
-#define NKSR_FILL(COMPACT, MAXL, MINB)                                                                          \
-  k_gram_fill<COMPACT, MAXL, MINB><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, val, rhs, \
-                                                                   diag, cursor)
+#define NKSR_FILL(COMPACT, MAXL, MINB)                                                                       \
+  k_gram_fill<COMPACT, MAXL, MINB, PLACED><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, val, \
+                                                                           rhs, diag, cursor, place)
   // 4 resident blocks per SM (64 registers) for depth <= 4; 5 blocks (48 registers) was measured
   // 1.7x slower (register starvation cuts the loads in flight per warp)
   if (svh->depth <= 4) {
@@ -572,6 +730,25 @@ int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_co
 #undef NKSR_FILL
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int nksr_gram_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c, const int32_t* cnt,
+                   const int64_t* rowptr, int32_t* col, float* val, float* rhs, float* diag, int32_t* cursor,
+                   void* stream) {
+  if (!cursor) return NKSR_E_INVALID;
+  return launch_fill<false>(svh, feat, c, cnt, rowptr, col, val, rhs, diag, cursor, PlaceArg<false>{}, stream);
+}
+
+int nksr_gram_fill_placed(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c,
+                          const int32_t* cnt, const int64_t* rowptr, const nksr_placement_t* placement,
+                          int32_t* col, float* val, float* rhs, float* diag, void* stream) {
+  if (!placement) return NKSR_E_INVALID;
+  PlaceArg<true> place;
+  place.t = *placement;
+  return launch_fill<true>(svh, feat, c, cnt, rowptr, col, val, rhs, diag, nullptr, place, stream);
 }
 
 int nksr_gram_sort_down(const int32_t* cnt, const int32_t* cnt_down, const int64_t* rowptr, const int32_t* rows,

@@ -64,6 +64,16 @@ __device__ __forceinline__ int find_key(const int64_t* __restrict__ keys, int64_
   return (lo < n && __ldg(keys + lo) == k) ? (int)lo : -1;
 }
 
+// first index whose key is >= k (n when none)
+__device__ __forceinline__ int64_t lower_bound_key(const int64_t* __restrict__ keys, int64_t n, int64_t k) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(keys + mid) < k) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

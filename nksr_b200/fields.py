@@ -15,6 +15,7 @@ The arithmetic is in libnksr_b200.so; the algorithm is fixed in DESIGN.md (SPEC 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from types import SimpleNamespace
 from typing import Optional
 
@@ -23,6 +24,11 @@ import torch
 from . import _lib
 from ._lib import call, stream_ptr
 from .svh import SparseFeatureHierarchy
+
+# where the transposed (finer-level) Gram entries go: "sorted" = atomic cursor + per-row segment sort,
+# "structural" = straight to the final slot from prefix tables (SPEC S6b).  solver_config['placement'] or the
+# NKSR_PLACEMENT environment variable override it.
+DEFAULT_PLACEMENT = "sorted"
 
 
 _TOTAL_MEMORY = {}
@@ -222,8 +228,30 @@ class KernelField(BaseField):
         tm = getattr(self, "_timer", None) or _lib.StageTimer(dev, enabled=False)
         tm.mark("kernel_rows")
         cnt = torch.empty(n, dtype=torch.int32, device=dev)
-        cnt_down = torch.empty(n, dtype=torch.int32, device=dev)
-        call("nksr_gram_count", svh.view(), cnt, cnt_down, st)
+        placement = self.solver_config.get("placement") or os.environ.get("NKSR_PLACEMENT") or DEFAULT_PLACEMENT
+        if placement not in ("sorted", "structural"):
+            raise ValueError("solver_config['placement'] must be 'sorted' or 'structural'")
+        place = None
+        if placement == "structural":
+            # transposed entries go straight to their final slot (SPEC S6b): per (fine level, offset) pair
+            # a rank table on the fine level and a 125-ancestor prefix table on the coarse level
+            cnt_down = torch.zeros(n, dtype=torch.int32, device=dev)
+            call("nksr_gram_count_own", svh.view(), cnt, st)
+            place = _lib.PlacementT()
+            for l in range(svh.depth - 1):
+                for k in range(1, svh.depth - l):
+                    n_lo, n_up = svh.num_voxels(l), svh.num_voxels(l + k)
+                    if n_lo == 0 or n_up == 0:
+                        continue
+                    rank8 = torch.empty((n_lo, 8), dtype=torch.int32, device=dev)
+                    classes = torch.empty((n_up, 27), dtype=torch.int32, device=dev)
+                    prefix = torch.empty((n_up, 125), dtype=torch.int32, device=dev)
+                    call("nksr_gram_place", svh.view(), l, k, rank8, classes, prefix, cnt_down, st)
+                    place.rank8[l][k], place.prefix[l][k] = rank8.data_ptr(), prefix.data_ptr()
+                    keep += [rank8, prefix]
+        else:
+            cnt_down = torch.empty(n, dtype=torch.int32, device=dev)
+            call("nksr_gram_count", svh.view(), cnt, cnt_down, st)
         rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
         nb = call("nksr_scan_workspace_bytes", n)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
@@ -262,13 +290,16 @@ class KernelField(BaseField):
         val = torch.empty(nnz, dtype=torch.float32, device=dev)
         rhs = torch.empty(n, dtype=torch.float32, device=dev)
         diag = torch.zeros(n, dtype=torch.float32, device=dev)
-        cursor = torch.zeros(n, dtype=torch.int32, device=dev)
-        call("nksr_gram_fill", svh.view(), self.feat_view(), cs, cnt, rowptr, col, val, rhs, diag, cursor, st)
+        if place is not None:
+            call("nksr_gram_fill_placed", svh.view(), self.feat_view(), cs, cnt, rowptr, place, col, val, rhs, diag, st)
+        else:
+            cursor = torch.zeros(n, dtype=torch.int32, device=dev)
+            call("nksr_gram_fill", svh.view(), self.feat_view(), cs, cnt, rowptr, col, val, rhs, diag, cursor, st)
         tm.mark("gram_fill")
-        # deterministic storage order of the transposed (finer-level) segments
+        # atomic-cursor variant: deterministic storage order of the transposed (finer-level) segments
         # (rows binned by segment length so that short rows do not pay for a large tile)
         offs = svh.offsets
-        if svh.depth > 1 and n > offs[1]:
+        if place is None and svh.depth > 1 and n > offs[1]:
             seg = cnt_down[offs[1]:]
             lo_b = 1
             for cap in (32, 128, 512, 1024, 2048, 4096, 8192, 16384):

@@ -135,6 +135,41 @@ def test_gram_assembly_matches_oracle(cuda, C, approx, compact, split):
     assert np.abs(_np(field.system.diag) - A_ref.diagonal()).max() <= RTOL_GRAM * scale
 
 
+@pytest.mark.parametrize("L,W,prune", [(4, 0.02, False), (2, 0.04, False), (5, 0.02, False), (3, 0.03, True)])
+def test_structural_placement_is_the_same_matrix(cuda, L, W, prune):
+    """SPEC S6b: placing the transposed entries from prefix tables (no atomics, no sort) stores exactly the
+    matrix of the atomic-cursor + sort variant -- same pattern, bitwise the same values, same row lengths --
+    and is itself run-to-run identical in storage order."""
+    import nksr_b200
+    xyz, _ = clouds.shapenet_like(3000)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    osvh = O.OracleSVH(W, L).build_point_splatting(xyz)
+    keys = list(osvh.keys)
+    if prune:                                               # a pruned finest level: childless level-1 voxels
+        keys[0] = keys[0][O.key_to_ijk(keys[0], 0)[:, 0] >= 0]
+        osvh = O.OracleSVH(W, L).build_from_keys(keys)
+    svh = nksr_b200.SparseFeatureHierarchy(W, L, cuda).build_from_keys([t(k) for k in keys])
+    feats = _feats(osvh, 4, 5)
+    nxyz = np.concatenate([osvh.centers(d) for d in range(min(2, L))])
+    nval = -(nxyz / np.linalg.norm(nxyz, axis=1, keepdims=True)).astype(np.float32)
+    pw, nw = 1e4 / xyz.shape[0], 1e4 / nxyz.shape[0] * W * W
+    out = {}
+    for placement in ("sorted", "structural", "structural"):
+        field = _field(cuda, svh, feats, False)
+        field.solver_config.update(keep_system=True, max_iter=0, placement=placement)
+        field.solve(t(xyz), t(nxyz), t(nval), pw, nw, 1.0)
+        s = field.system
+        out.setdefault(placement, []).append((_np(s.rowptr).copy(), _np(s.col).copy(), _np(s.val).copy(), _gpu_csr(field)))
+    (rp_s, _, _, A_s), (rp_a, col_a, val_a, A_a), (rp_b, col_b, val_b, _) = out["sorted"][0], *out["structural"]
+    assert np.array_equal(rp_s, rp_a) and A_s.nnz == A_a.nnz
+    A_s.sum_duplicates(); A_a.sum_duplicates()
+    assert A_a.nnz == rp_a[-1] and (A_s != A_a).nnz == 0                # no duplicate slot, identical entries
+    assert np.array_equal(rp_a, rp_b) and np.array_equal(col_a, col_b) and np.array_equal(val_a, val_b)
+    P = O.structural_pattern(osvh)
+    Ab = A_a.copy(); Ab.data[:] = 1
+    assert Ab.nnz == P.nnz and (Ab - P).count_nonzero() == 0
+
+
 def test_gram_position_only_and_determinism(cuda):
     field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda, 4, False, 2000, 0.05, 3, "sphere")
     field.solver_config.update(keep_system=True, max_iter=0)
