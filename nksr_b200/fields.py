@@ -28,7 +28,7 @@ from .svh import SparseFeatureHierarchy
 # where the transposed (finer-level) Gram entries go: "sorted" = atomic cursor + per-row segment sort,
 # "structural" = straight to the final slot from prefix tables (SPEC S6b).  solver_config['placement'] or the
 # NKSR_PLACEMENT environment variable override it.
-DEFAULT_PLACEMENT = "sorted"
+DEFAULT_PLACEMENT = "structural"
 
 
 _TOTAL_MEMORY = {}
