@@ -4,7 +4,9 @@
 //
 // Layout (DESIGN.md SPEC S6): unknowns are ordered level-major, Morton inside a level.  Row
 // (l,i) stores, in this order, [same-level 125-stencil | coarser level l+1 (<=64) | ... | level
-// L-1 | finer-level entries (transposes)].  Only ACTIVE column voxels are stored.
+// L-1 | finer-level entries (transposes)].  Only ACTIVE column voxels are stored.  The transposed copies
+// go straight to their final slot from two prefix tables (k_place_rank / k_place_prefix, SPEC S6b); the
+// older atomic-cursor + segment-sort variant is kept behind solver_config['placement'] = 'sorted'.
 //
 // Numeric phase: one warp per row.  For each of the 27 voxels u around i, the constraint rows
 // whose containing voxel is u form one contiguous range (locations are Morton sorted); every
