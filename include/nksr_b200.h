@@ -105,10 +105,7 @@ NKSR_API int nksr_row_ranges(const int32_t* base_l, int64_t m, int32_t* range, i
  *   mode 0: value rows    e[(m*L + l)*32 + s]             (position constraints)
  *   mode 1: gradient rows e[((m*L + l)*3 + a)*32 + s]     (normal constraints)
  *   mode 2: compact gradient rows e[(m*L + l)*32 + s], s<27: <phi,z_s>, s=27..29: tau
- *           (approx_kernel_grad only; the assembly rebuilds the three rows)
- *   modes 3 / 4 (experimental, depth <= 4): the rows of modes 0 / 1 with the level as the fastest index,
- *           e[(m*32 + s)*4 + l] and e[((m*3 + a)*32 + s)*4 + l] (levels >= depth are zero), so that one
- *           128-bit load per lane brings a slot's value on all four levels                  */
+ *           (approx_kernel_grad only; the assembly rebuilds the three rows)              */
 NKSR_API int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* xyz,
                     const int32_t* base, int64_t m, int mode, int approx_kernel_grad, float* e,
                     void* stream);
@@ -135,8 +132,6 @@ typedef struct {
   const float* mblocks;
   int32_t split_level;
   int64_t mblock_off[NKSR_MAX_DEPTH];
-  /* 1: e_pos / e_nrm hold level-interleaved rows (nksr_build_rows modes 3 / 4; depth <= 4, not compact) */
-  int32_t interleaved;
 } nksr_constraints_t;
 /* floats needed for the blocks of levels >= split_level */
 NKSR_API int64_t nksr_gram_block_floats(const nksr_svh_t* svh, int split_level);

@@ -34,8 +34,7 @@ class ConstraintsT(C.Structure):
     _fields_ = [("e_pos", C.c_void_p), ("range_pos", C.c_void_p), ("n_pos", C.c_int64), ("w_pos", C.c_float),
                 ("e_nrm", C.c_void_p), ("range_nrm", C.c_void_p), ("t_nrm", C.c_void_p), ("n_nrm", C.c_int64),
                 ("w_nrm", C.c_float), ("w_reg", C.c_float), ("nrm_compact", C.c_int32),
-                ("mblocks", C.c_void_p), ("split_level", C.c_int32), ("mblock_off", C.c_int64 * MAX_DEPTH),
-                ("interleaved", C.c_int32)]
+                ("mblocks", C.c_void_p), ("split_level", C.c_int32), ("mblock_off", C.c_int64 * MAX_DEPTH)]
 
 
 class PlacementT(C.Structure):

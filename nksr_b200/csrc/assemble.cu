@@ -318,57 +318,7 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
   blk[27 * NKSR_ROW_STRIDE + lane] = bvec;
 }
 
-// component `lev` (warp-uniform) of a level-interleaved row element
-__device__ __forceinline__ float comp4(const float4& v, int lev) {
-  return lev == 0 ? v.x : (lev == 1 ? v.y : (lev == 2 ? v.z : v.w));
-}
-
-// k_gram_blocks on level-interleaved rows (constraints.interleaved, depth <= 4): one 128-bit load per
-// lane brings both levels of the product
-__global__ void __launch_bounds__(kWarps * 32)
-k_gram_blocks4(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks) {
-  const int lane = threadIdx.x & 31;
-  int64_t w = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
-  int l = cs.split_level;
-  while (l < svh.depth && w >= svh.n[l] * (svh.depth - l)) { w -= svh.n[l] * (svh.depth - l); ++l; }
-  if (l >= svh.depth) return;
-  const int nlev = svh.depth - l;
-  const int u = (int)(w / nlev), k = (int)(w - (int64_t)u * nlev);
-  float m[28];
-#pragma unroll
-  for (int s = 0; s < 28; ++s) m[s] = 0.f;
-  float bvec = 0.f;
-  if (cs.range_pos) {
-    const int32_t* rp = cs.range_pos + 2 * (svh.offset[l] + u);
-    const int pb = __ldg(rp), pe = __ldg(rp + 1);
-    const float4* e4 = reinterpret_cast<const float4*>(cs.e_pos) + lane;
-    for (int q = pb; q < pe; ++q) {
-      const float4 v = __ldg(e4 + (int64_t)q * 32);
-      const float e0 = comp4(v, l);
-      gram_block_update(m, cs.w_pos * e0, comp4(v, l + k));
-    }
-  }
-  if (cs.range_nrm) {
-    const int32_t* rn = cs.range_nrm + 2 * (svh.offset[l] + u);
-    const int nb = __ldg(rn), ne = __ldg(rn + 1);
-    const float4* e4 = reinterpret_cast<const float4*>(cs.e_nrm) + lane;
-    for (int q = nb; q < ne; ++q) {
-#pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        const float4 v = __ldg(e4 + ((int64_t)q * 3 + ax) * 32);
-        const float el = cs.w_nrm * comp4(v, l);
-        if (k == 0) bvec = fmaf(el, __ldg(cs.t_nrm + (int64_t)q * 3 + ax), bvec);
-        gram_block_update(m, el, comp4(v, l + k));
-      }
-    }
-  }
-  float* blk = mblocks + (cs.mblock_off[l] + (int64_t)u * nlev + k) * kBlockFloats;
-#pragma unroll
-  for (int s = 0; s < 27; ++s) blk[s * NKSR_ROW_STRIDE + lane] = m[s];
-  blk[27 * NKSR_ROW_STRIDE + lane] = bvec;
-}
-
-template <bool COMPACT, int MAXL, int MINB, bool PLACED, bool INTER = false>
+template <bool COMPACT, int MAXL, int MINB, bool PLACED>
 __global__ void __launch_bounds__(kWarps * 32, MINB)
 k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_total,
             const int32_t* __restrict__ cnt, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col_out,
@@ -434,43 +384,6 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
 #pragma unroll
       for (int k = 0; k < MAXL; ++k)
         if (k <= nup) r[k] = __ldg(blk + (int64_t)k * kBlockFloats + si * NKSR_ROW_STRIDE + lane);
-    } else if (INTER) {
-      // level-interleaved rows (MAXL == 4, not COMPACT): one 128-bit load per lane and constraint line
-      // brings the slot's value on the four ABSOLUTE levels; two packed FMAs consume it
-      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
-      const float4* e4 = reinterpret_cast<const float4*>(cs.e_pos) + lane;
-      const float* ea = cs.e_pos + si * 4 + l;
-      for (int q = pb; q < pe; ++q) {
-        const float a = cs.w_pos * __ldg(ea + (int64_t)q * 128);
-        const float4 v = __ldg(e4 + (int64_t)q * 32);
-        const float2 a2 = make_float2(a, a);
-        s01 = __ffma2_rn(a2, make_float2(v.x, v.y), s01);
-        s23 = __ffma2_rn(a2, make_float2(v.z, v.w), s23);
-      }
-      const float4* n4 = reinterpret_cast<const float4*>(cs.e_nrm) + lane;
-      const float* na = cs.e_nrm + si * 4 + l;
-      for (int q = nb; q < ne; ++q) {
-        const float* t = cs.t_nrm + (int64_t)q * 3;
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          const float a = cs.w_nrm * __ldg(na + ((int64_t)q * 3 + ax) * 128);
-          bsum = fmaf(a, __ldg(t + ax), bsum);
-          const float4 v = __ldg(n4 + ((int64_t)q * 3 + ax) * 32);
-          const float2 a2 = make_float2(a, a);
-          s01 = __ffma2_rn(a2, make_float2(v.x, v.y), s01);
-          s23 = __ffma2_rn(a2, make_float2(v.z, v.w), s23);
-        }
-      }
-      // absolute level -> offset k = level - l
-      const float ra[4] = {s01.x, s01.y, s23.x, s23.y};
-#pragma unroll
-      for (int k = 0; k < MAXL && k < 4; ++k) {
-        float x = 0.f;
-#pragma unroll
-        for (int lev = k; lev < 4; ++lev)
-          if (lev - k == l) x = ra[lev];
-        r[k] = x;
-      }
     } else {
     // packed fp32 FMAs (FFMA2, sm_100): two levels per instruction, same IEEE result per lane
     float2 r2[MAXL / 2];
@@ -784,10 +697,7 @@ int nksr_gram_blocks(const nksr_svh_t* svh, const nksr_constraints_t* c, float* 
   for (int l = c->split_level; l < svh->depth; ++l) warps += svh->n[l] * (svh->depth - l);
   if (warps == 0) return NKSR_OK;
   const int grid = grid_for(warps, kWarps);
-  if (c->interleaved) {
-    if (svh->depth > 4) return NKSR_E_INVALID;
-    k_gram_blocks4<<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
-  } else if (svh->depth <= 4)
+  if (svh->depth <= 4)
     k_gram_blocks<4><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
   else
     k_gram_blocks<NKSR_MAX_DEPTH><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
@@ -814,11 +724,7 @@ int launch_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_const
                                                                            rhs, diag, cursor, place)
   // 4 resident blocks per SM (64 registers) for depth <= 4; 5 blocks (48 registers) was measured
   // 1.7x slower (register starvation cuts the loads in flight per warp)
-  if (c->interleaved) {
-    if (svh->depth > 4 || c->nrm_compact) return NKSR_E_INVALID;
-    k_gram_fill<false, 4, 4, PLACED, true><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, val,
-                                                                          rhs, diag, cursor, place);
-  } else if (svh->depth <= 4) {
+  if (svh->depth <= 4) {
     if (c->nrm_compact) NKSR_FILL(true, 4, 4); else NKSR_FILL(false, 4, 4);
   } else {
     if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH, 2); else NKSR_FILL(false, NKSR_MAX_DEPTH, 2);

@@ -53,46 +53,6 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
   }
 }
 
-// Level-interleaved rows (modes 3 / 4, depth <= 4): same values as modes 0 / 1, but a lane keeps its
-// slot's value on the four levels and writes them as one float4 -- e[(m*ROWS + a)*32 + lane] -- so that
-// the assembly gets a slot on all levels with one 128-bit load instead of four 32-bit ones.
-template <bool GRAD>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_build_rows4(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, const int32_t* __restrict__ base,
-              int64_t m, bool fullgrad, float4* __restrict__ e) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
-  if (i >= m) return;
-  constexpr int ROWS = GRAD ? 3 : 1;
-  const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
-  float v[ROWS][4];
-#pragma unroll
-  for (int a = 0; a < ROWS; ++a)
-#pragma unroll
-    for (int l = 0; l < 4; ++l) v[a][l] = 0.f;
-#pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    if (l < svh.depth) {
-      const int b = __ldg(base + (int64_t)l * m + i);
-      if (b >= 0) {
-        const float wl = svh.voxel_size * (float)(1 << l);
-        LaneKernel r = eval_level_lane<GRAD>(svh.keys[l], svh.nbr27[l], feat.z[l], feat.channels, l, wl, px, py, pz,
-                                             b, fullgrad, lane);
-        if constexpr (GRAD) {
-          v[0][l] = r.dk[0];
-          v[1][l] = r.dk[1];
-          v[2][l] = r.dk[2];
-        } else {
-          v[0][l] = r.k;
-        }
-      }
-    }
-  }
-  float4* out = e + (int64_t)i * ROWS * 32 + lane;
-#pragma unroll
-  for (int a = 0; a < ROWS; ++a) out[a * 32] = make_float4(v[a][0], v[a][1], v[a][2], v[a][3]);
-}
-
 // one warp per query: f(x) = sum_l sum_s alpha * K ; containing voxels found by top search + descent
 template <bool GRAD>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -184,16 +144,6 @@ int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float*
   if (m == 0) return NKSR_OK;
   const int grid = grid_for(m, kWarpsPerBlock);
   cudaStream_t s = as_stream(stream);
-  if (mode == 3 || mode == 4) {  // level-interleaved rows
-    if (svh->depth > 4) return NKSR_E_INVALID;
-    float4* e4 = reinterpret_cast<float4*>(e);
-    if (mode == 3)
-      k_build_rows4<false><<<grid, kWarpsPerBlock * 32, 0, s>>>(*svh, *feat, xyz, base, m, false, e4);
-    else
-      k_build_rows4<true><<<grid, kWarpsPerBlock * 32, 0, s>>>(*svh, *feat, xyz, base, m, !approx_kernel_grad, e4);
-    NKSR_CHECK_LAUNCH();
-    return NKSR_OK;
-  }
   if (mode < 0 || mode > 2 || (mode == 2 && !approx_kernel_grad)) return NKSR_E_INVALID;
   const bool full = mode == 1 && !approx_kernel_grad;
 #define NKSR_ROWS(MODE, MAXL) \

@@ -29,10 +29,6 @@ from .svh import SparseFeatureHierarchy
 # "structural" = straight to the final slot from prefix tables (SPEC S6b).  solver_config['placement'] or the
 # NKSR_PLACEMENT environment variable override it.
 DEFAULT_PLACEMENT = "structural"
-# layout of the constraint rows E: "lines" = one 128-byte line per (location, level[, axis]); "interleaved"
-# (experimental, depth <= 4) = level as the fastest index, one 128-bit load per lane covers the four levels.
-# solver_config['row_layout'] or NKSR_ROW_LAYOUT override it.
-DEFAULT_ROW_LAYOUT = "lines"
 
 
 _TOTAL_MEMORY = {}
@@ -162,11 +158,8 @@ class KernelField(BaseField):
         offs = svh.offsets
         for l in range(svh.depth):
             call("nksr_row_ranges", base[l], m, ranges[offs[l]:], svh.num_voxels(l), st)
-        if mode in (3, 4):                                                           # level-interleaved rows
-            e = torch.empty((m, 3 if mode == 4 else 1, _lib.ROW_STRIDE, 4), dtype=torch.float32, device=dev)
-        else:
-            width = _lib.ROW_STRIDE * (3 if mode == 1 else 1)
-            e = torch.empty((m, svh.depth, width), dtype=torch.float32, device=dev)  # location-major
+        width = _lib.ROW_STRIDE * (3 if mode == 1 else 1)
+        e = torch.empty((m, svh.depth, width), dtype=torch.float32, device=dev)      # location-major
         call("nksr_build_rows", svh.view(), self.feat_view(), xs, base, m, mode,
              int(self.approx_kernel_grad), e, st)
         return xs, ex, base, ranges, e
@@ -211,13 +204,7 @@ class KernelField(BaseField):
         pos_xyz = pos_xyz.detach().to(dev, torch.float32).contiguous()
         cs = _lib.ConstraintsT()
         keep = []
-        compact = bool(self.approx_kernel_grad and self.solver_config.get("compact_rows", False))
-        layout = self.solver_config.get("row_layout") or os.environ.get("NKSR_ROW_LAYOUT") or DEFAULT_ROW_LAYOUT
-        if layout not in ("lines", "interleaved"):
-            raise ValueError("solver_config['row_layout'] must be 'lines' or 'interleaved'")
-        inter = layout == "interleaved" and svh.depth <= 4 and not compact
-        cs.interleaved = int(inter)
-        _, _, _, range_pos, e_pos = self._sorted_rows(pos_xyz, 3 if inter else 0)
+        _, _, _, range_pos, e_pos = self._sorted_rows(pos_xyz, 0)
         keep += [range_pos, e_pos]
         cs.e_pos, cs.range_pos, cs.n_pos, cs.w_pos = e_pos.data_ptr(), range_pos.data_ptr(), pos_xyz.shape[0], float(pos_weight)
         if normal_xyz is not None and normal_xyz.shape[0] > 0:
@@ -227,7 +214,7 @@ class KernelField(BaseField):
             # compact gradient rows (one line instead of three per location and level) save 2/3 of
             # the row memory but cost ALU in the assembly; measured slower on B200 (profiles/r1c),
             # so they are opt-in for clouds that would not fit otherwise
-            nrm_mode = 4 if inter else (2 if compact else 1)
+            nrm_mode = 2 if (self.approx_kernel_grad and self.solver_config.get("compact_rows", False)) else 1
             _, t_nrm, _, range_nrm, e_nrm = self._sorted_rows(normal_xyz, nrm_mode, normal_value)
             cs.nrm_compact = int(nrm_mode == 2)
             keep += [t_nrm, range_nrm, e_nrm]
