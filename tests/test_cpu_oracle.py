@@ -147,6 +147,30 @@ def test_library_exports_every_declared_symbol():
     assert lib.nksr_version
 
 
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The structs that cross the C-ABI by pointer: sizeof and every field offset of the ctypes mirror in
+    nksr_b200/_lib.py equal what a C compiler makes of include/nksr_b200.h (the header is plain C)."""
+    import subprocess
+    import nksr_b200._lib as L
+    pairs = {"nksr_svh_t": L.SvhT, "nksr_feat_t": L.FeatT, "nksr_constraints_t": L.ConstraintsT,
+             "nksr_placement_t": L.PlacementT}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nksr_b200.h"', "int main(void) {"]
+    for cname, mirror in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, mirror in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(mirror), cname
+        for fname, _ in mirror._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(mirror, fname).offset, f"{cname}.{fname}"
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "nksr_b200")):
         for fn in files:
