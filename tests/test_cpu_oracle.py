@@ -147,6 +147,32 @@ def test_library_exports_every_declared_symbol():
     assert lib.nksr_version
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/nksr_b200.h against the argument kinds nksr_b200/_lib.py binds: same count,
+    pointer where the header has a pointer, the right scalar width elsewhere."""
+    import nksr_b200._lib as L
+    header = open(os.path.join(ROOT, "include", "nksr_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"NKSR_API\s+([\w\s\*]+?)\b(nksr_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) == len(L._SIGNATURES)
+    scalar = {"int64_t": "q", "int32_t": "i", "int": "i", "float": "f", "size_t": "z"}
+    struct = {"nksr_svh_t": "S", "nksr_feat_t": "F", "nksr_constraints_t": "K", "nksr_placement_t": "P"}
+    for ret, name, params in protos:
+        kinds = L._SIGNATURES[name][1]
+        plist = [p.strip() for p in params.replace("\n", " ").split(",")] if params.strip() not in ("", "void") else []
+        assert len(plist) == len(kinds), name
+        for p, k in zip(plist, kinds):
+            if "*" in p:
+                base = re.sub(r"\bconst\b", "", p).split("*")[0].strip()
+                want = struct.get(base, "d" if base == "double" else "p")
+                assert k == want, (name, p, k)
+            else:
+                assert k == scalar[p.split()[-2] if len(p.split()) > 1 else p], (name, p, k)
+        rk = L._SIGNATURES[name][0]
+        ret = ret.strip()
+        assert rk == {"int": "i", "size_t": "z", "int64_t": "q", "const char*": "s", "const char *": "s"}[ret], (name, ret)
+
+
 def test_ctypes_mirrors_match_the_header_layout(tmp_path):
     """The structs that cross the C-ABI by pointer: sizeof and every field offset of the ctypes mirror in
     nksr_b200/_lib.py equal what a C compiler makes of include/nksr_b200.h (the header is plain C)."""
