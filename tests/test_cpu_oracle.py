@@ -173,6 +173,34 @@ def test_ctypes_signatures_match_the_header_prototypes():
         assert rk == {"int": "i", "size_t": "z", "int64_t": "q", "const char*": "s", "const char *": "s"}[ret], (name, ret)
 
 
+def test_every_python_call_site_passes_the_declared_number_of_arguments():
+    """Static check of the host mirror: each call("nksr_...", ...) in nksr_b200/*.py, bench.py, tools/ and
+    __graft_entry__.py has as many arguments as the entry point declares (paths a CPU run never executes)."""
+    import ast
+    import nksr_b200._lib as L
+    files = [os.path.join(ROOT, "nksr_b200", f) for f in os.listdir(os.path.join(ROOT, "nksr_b200")) if f.endswith(".py")]
+    files += [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    files += [os.path.join(ROOT, "tools", f) for f in os.listdir(os.path.join(ROOT, "tools")) if f.endswith(".py")]
+    seen = 0
+    for path in files:
+        for node in ast.walk(ast.parse(open(path).read())):
+            if not isinstance(node, ast.Call) or not node.args:
+                continue
+            fn = node.func
+            fname = fn.id if isinstance(fn, ast.Name) else (fn.attr if isinstance(fn, ast.Attribute) else None)
+            first = node.args[0]
+            if fname != "call" or not (isinstance(first, ast.Constant) and isinstance(first.value, str)
+                                       and first.value.startswith("nksr_")):
+                continue
+            assert first.value in L._SIGNATURES, (path, first.value)
+            if any(isinstance(a, ast.Starred) for a in node.args):
+                continue
+            assert len(node.args) - 1 == len(L._SIGNATURES[first.value][1]), (os.path.basename(path), node.lineno,
+                                                                             first.value)
+            seen += 1
+    assert seen >= 50
+
+
 def test_ctypes_mirrors_match_the_header_layout(tmp_path):
     """The structs that cross the C-ABI by pointer: sizeof and every field offset of the ctypes mirror in
     nksr_b200/_lib.py equal what a C compiler makes of include/nksr_b200.h (the header is plain C)."""
