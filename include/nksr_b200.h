@@ -171,13 +171,37 @@ NKSR_API int nksr_gram_fill_placed(const nksr_svh_t* svh, const nksr_feat_t* fea
 NKSR_API int nksr_spmv(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
               float* y, int64_t n, void* stream);
 NKSR_API size_t nksr_pcg_workspace_bytes(int64_t n);
-/* Jacobi-PCG from x=0. info (host double[4]): [0]=iterations, [1]=relative residual; with
- * profile != 0 also [2]=total ms of the SpMV launches (CUDA events on `stream`, first 512
- * iterations) and [3]=number of launches timed. */
+/* Jacobi-PCG from x=0 with the convergence test on the device and the iterations replayed from a CUDA graph
+ * of `check_every` iterations (one host read-back per graph launch).  info (host double[5]): [0]=iterations,
+ * [1]=relative residual, [4]=status (0 converged, 1 max_iter reached, 2 NaN/breakdown); with profile != 0
+ * (plain launches) also [2]=total ms of the live SpMV launches (CUDA events on `stream`, first 512 iterations)
+ * and [3]=number of launches timed. */
 NKSR_API int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val,
                    const float* diag, const float* b, float* x, int64_t n, float tol,
                    int max_iter, int check_every, int profile, void* ws, size_t ws_bytes,
                    double* info, void* stream);
+
+/* ---- e: step kernels of the multi-GPU solve (one global system, SURVEY section 8e mapping B).  A
+ * Chronopoulos-Gear arrangement of the same Jacobi-PCG: per iteration ONE halo exchange of u = M^-1 r, one
+ * SpMV on the owned rows and ONE fused all-reduce of red[3] = {(r,u), (w,u), (r,r)}; the caller issues the
+ * collective (NCCL) on `red` between nksr_dcg_spmv_dots and nksr_dcg_update.  owned[i] != 0: row i belongs to
+ * this rank.  All vectors are caller-owned (n floats each); ws: nksr_dcg_workspace_bytes(); red: 3 doubles. */
+NKSR_API size_t nksr_dcg_workspace_bytes(void);
+/* x=0, r=b, u=r/diag on owned rows; red[0] = local (b,b) -> all-reduce red, then nksr_dcg_begin */
+NKSR_API int nksr_dcg_init(const float* diag, const float* b, const uint8_t* owned, float* x, float* r, float* u,
+                  float* p, float* s, int64_t n, void* ws, size_t ws_bytes, double* red, void* stream);
+NKSR_API int nksr_dcg_begin(void* ws, const double* red, float tol, int max_iter, void* stream);
+/* w = A u on owned rows, red = local {(r,u), (w,u), (r,r)}; no-op once the solve is over */
+NKSR_API int nksr_dcg_spmv_dots(const int64_t* rowptr, const int32_t* col, const float* val, const uint8_t* owned,
+                       const float* r, const float* u, float* w, int64_t n, void* ws, double* red, void* stream);
+/* red = all-reduced sums: convergence verdict on the device, else p,s,x,r,u advance one iteration */
+NKSR_API int nksr_dcg_update(const float* diag, const uint8_t* owned, float* x, float* r, float* u, const float* w,
+                    float* p, float* s, int64_t n, void* ws, const double* red, void* stream);
+/* synchronising read-back: info (host double[4]) = iterations, relative residual, status as above, done flag */
+NKSR_API int nksr_dcg_status(void* ws, double* info, void* stream);
+/* halo packing: out[i] = src[idx[i]] / dst[idx[i]] = src[i] (idx: int64) */
+NKSR_API int nksr_gather_f32(const float* src, const int64_t* idx, int64_t m, float* out, void* stream);
+NKSR_API int nksr_scatter_f32(const float* src, const int64_t* idx, int64_t m, float* dst, void* stream);
 
 /* ---- a5: field.evaluate_f (models/loss.py:189-198,225) ---- */
 NKSR_API int nksr_evaluate(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* alpha,

@@ -80,6 +80,14 @@ _SIGNATURES = {
     "nksr_spmv": ("i", "pppppqp"),
     "nksr_pcg_workspace_bytes": ("z", "q"),
     "nksr_pcg_solve": ("i", "pppppp" + "qfiii" + "pzdp"),
+    "nksr_dcg_workspace_bytes": ("z", ""),
+    "nksr_dcg_init": ("i", "pppppppp" + "q" + "pz" + "pp"),
+    "nksr_dcg_begin": ("i", "ppfip"),
+    "nksr_dcg_spmv_dots": ("i", "ppppppp" + "q" + "ppp"),
+    "nksr_dcg_update": ("i", "pppppppp" + "q" + "ppp"),
+    "nksr_dcg_status": ("i", "pdp"),
+    "nksr_gather_f32": ("i", "ppqpp"),
+    "nksr_scatter_f32": ("i", "ppqpp"),
     "nksr_evaluate": ("i", "SFppqiippp"),
     "nksr_mesh_cell_flags": ("i", "Spp"),
     "nksr_mesh_stage0_cells": ("i", "Sppipp"),
@@ -156,7 +164,15 @@ def call(name: str, *args):
     if len(kinds) != len(args):
         raise TypeError(f"{name}: expected {len(kinds)} arguments, got {len(args)}")
     fn = getattr(lib, name)
-    rc = fn(*[_conv(k, a) for k, a in zip(kinds, args)])
+    conv = [_conv(k, a) for k, a in zip(kinds, args)]
+    # the library launches on the CURRENT device: make it the device that owns the tensors (the stream
+    # argument already belongs to it), so cuda:1 fields work while cuda:0 is current
+    dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+    if dev is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = fn(*conv)
+    else:
+        rc = fn(*conv)
     if _SIGNATURES[name][0] == "i" and rc != 0:
         raise NksrError(f"{name} failed: {lib.nksr_error_string(rc).decode()} ({rc})")
     return rc

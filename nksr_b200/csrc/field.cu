@@ -24,6 +24,13 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
   constexpr bool GRAD = MODE == 1;
   constexpr int ROWS = GRAD ? 3 : 1;
   const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
+  // half-voxel coordinates of the point (SPEC S1, same expression as nksr_locate): the containing voxel on
+  // level l is (h + 2^20) >> (l+1), so no key has to be loaded and decoded per level
+  const float half_w = svh.voxel_size * 0.5f;
+  const int hx = (int)floorf(__fdiv_rn(px, half_w)) + NKSR_HALF_OFFSET;
+  const int hy = (int)floorf(__fdiv_rn(py, half_w)) + NKSR_HALF_OFFSET;
+  const int hz = (int)floorf(__fdiv_rn(pz, half_w)) + NKSR_HALF_OFFSET;
+  const double inv0 = 1.0 / (double)svh.voxel_size;
   // location-major layout [m][L][rows][32]: all lines of one location are contiguous, so the
   // assembly kernel reaches them with compile-time offsets from one base pointer
   float* out0 = e + (int64_t)i * svh.depth * ROWS * NKSR_ROW_STRIDE;
@@ -37,8 +44,8 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
         if (GRAD) { out[32 + lane] = 0.f; out[64 + lane] = 0.f; }
       } else {
         const float wl = svh.voxel_size * (float)(1 << l);
-        LaneKernel r = eval_level_lane<GRAD>(svh.keys[l], svh.nbr27[l], feat.z[l], feat.channels, l, wl, px, py, pz,
-                                             b, fullgrad, lane);
+        LaneKernel r = eval_level_lane<GRAD>(svh.nbr27[l], feat.z[l], feat.channels, l, wl, inv0, px, py, pz, b,
+                                             hx >> (l + 1), hy >> (l + 1), hz >> (l + 1), fullgrad, lane);
         if (GRAD) {
           out[lane] = r.dk[0];
           out[32 + lane] = r.dk[1];
@@ -75,6 +82,7 @@ k_evaluate(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ alpha, co
     }
   }
   const int L = svh.depth;
+  const double inv0 = 1.0 / (double)svh.voxel_size;
   int idx = -1;
   if (!bad && svh.n[L - 1] > 0)
     idx = find_key(svh.keys[L - 1], svh.n[L - 1], morton3(u[0] >> L, u[1] >> L, u[2] >> L));
@@ -82,8 +90,8 @@ k_evaluate(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ alpha, co
   for (int l = L - 1; l >= 0; --l) {
     if (idx < 0) break;  // parent closure: nothing active below
     const float wl = svh.voxel_size * (float)(1 << l);
-    LaneKernel r = eval_level_lane<GRAD>(svh.keys[l], svh.nbr27[l], feat.z[l], feat.channels, l, wl, px, py, pz,
-                                         idx, fullgrad, lane);
+    LaneKernel r = eval_level_lane<GRAD>(svh.nbr27[l], feat.z[l], feat.channels, l, wl, inv0, px, py, pz, idx,
+                                         u[0] >> (l + 1), u[1] >> (l + 1), u[2] >> (l + 1), fullgrad, lane);
     float a = r.nb >= 0 ? __ldg(alpha + svh.offset[l] + r.nb) : 0.f;
     accf = fmaf(a, r.k, accf);
     if (GRAD) {

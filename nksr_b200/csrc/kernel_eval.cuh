@@ -42,18 +42,18 @@ __device__ __forceinline__ void axis_weights(float tau, int d, float& b, float& 
 
 // All 32 lanes must call.  base >= 0.  GRAD: also the gradient; FULLGRAD: include the
 // grad(phi) term (approx_kernel_grad == false).
+// (ux,uy,uz): offset-space coordinates of the containing voxel `base` -- the caller already has them from the
+// point's own quantisation ((h + 2^20) >> (level+1), SPEC S1), so the key is neither loaded nor decoded;
+// inv0 = 1 / voxel_size in fp64, computed once per location (1/(W 2^l) = inv0 * 2^-l exactly).
 template <bool GRAD>
-__device__ __forceinline__ LaneKernel eval_level_lane(const int64_t* __restrict__ keys,
-                                                      const int32_t* __restrict__ nbr27,
+__device__ __forceinline__ LaneKernel eval_level_lane(const int32_t* __restrict__ nbr27,
                                                       const float* __restrict__ z, int C, int level,
-                                                      float wl, float px, float py, float pz, int base,
-                                                      bool fullgrad, int lane) {
+                                                      float wl, double inv0, float px, float py, float pz, int base,
+                                                      int ux, int uy, int uz, bool fullgrad, int lane) {
   LaneKernel r;
-  int ux, uy, uz;
-  morton3_decode(__ldg(keys + base), ux, uy, uz);
   const int off = level_offset(level);
   // local coordinate in voxel units; the subtraction is done in fp64 to avoid cancellation
-  const double inv = 1.0 / (double)wl;
+  const double inv = inv0 * (1.0 / (double)(1 << level));
   float tx = (float)((double)px * inv - ((double)(ux - off) + 0.5));
   float ty = (float)((double)py * inv - ((double)(uy - off) + 0.5));
   float tz = (float)((double)pz * inv - ((double)(uz - off) + 0.5));

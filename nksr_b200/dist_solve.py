@@ -9,16 +9,20 @@ points within a few coarsest voxels, the rows of owned unknowns are bit-for-bit 
 single-GPU system; the halo unknowns only serve as columns.  Conjugate gradients then run on the
 union of the owned rows:
 
-    per iteration:  halo exchange of p (neighbour send/recv of the boundary entries)
-                    SpMV on the local CSR (nksr_spmv, the same hand-written kernel)
-                    two fp64 dot products, each ONE all-reduce of a device scalar
+    per iteration:  halo exchange of u = M^-1 r (pack kernel -> ONE all-to-all -> unpack kernel)
+                    SpMV on the owned rows of the local CSR + the three local dot products
+                    ONE fused fp64 all-reduce of {(r,u), (w,u), (r,r)}
+                    one fused vector-update kernel (Chronopoulos-Gear recurrences, verdict on the device)
 
-The vector updates of this driver are torch ops (a handful of n-vector passes next to an
-8·nnz-byte SpMV); nothing is synchronised with the host except the residual test.
-Works with `nccl` on GPUs; the key matching / ownership logic is plain tensor code tested on gloo.
+Everything between the two collectives is a hand-written kernel of libnksr_b200.so (csrc/solve.cu,
+`nksr_dcg_*`); the host only enqueues, and reads the device-side verdict every `check_every`
+iterations.  Points travel once, by an all-to-all to the ranks whose slab (+ halo) contains them, so
+no rank ever holds the whole cloud.  Works with `nccl` on GPUs; the key matching / ownership /
+exchange logic is plain tensor code tested on gloo (CPU tensors).
 """
 from __future__ import annotations
 
+import ctypes as C
 from types import SimpleNamespace
 from typing import List, Optional
 
@@ -31,11 +35,72 @@ from .fields import KernelField, LayerField
 from .svh import SparseFeatureHierarchy, SparseIndexGrid
 
 
-def slab_bounds(coord: torch.Tensor, world: int, quantum: float) -> List[float]:
+def _world(group=None):
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def _rank(group=None):
+    return dist.get_rank(group) if dist.is_initialized() else 0
+
+
+def all_to_all_rows(chunks: List[torch.Tensor], group=None) -> List[torch.Tensor]:
+    """Variable-size all-to-all of row blocks (same trailing shape and dtype): chunks[r] goes to rank r;
+    returns what every rank sent here.  NCCL: one all_to_all_single for the counts and one for the payload;
+    other backends (gloo CPU tests): point-to-point."""
+    world, rank = _world(group), _rank(group)
+    if world == 1:
+        return [chunks[0]]
+    dev, dtype, tail = chunks[0].device, chunks[0].dtype, tuple(chunks[0].shape[1:])
+    width = 1
+    for t in tail:
+        width *= t
+    send_counts = torch.tensor([c.shape[0] for c in chunks], dtype=torch.int64, device=dev)
+    if dist.get_backend(group) == "nccl":
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        rc = recv_counts.tolist()
+        send = torch.cat([c.reshape(c.shape[0], width) for c in chunks]).contiguous()
+        recv = torch.empty((sum(rc), width), dtype=dtype, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=send_counts.tolist(), group=group)
+        return [t.reshape((t.shape[0],) + tail) for t in torch.split(recv, rc)]
+    allc = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(allc, send_counts, group=group)
+    out, ops = [None] * world, []
+    for r in range(world):
+        n_in = int(allc[r][rank])
+        if r == rank:
+            out[r] = chunks[r]
+            continue
+        out[r] = torch.empty((n_in,) + tail, dtype=dtype, device=dev)
+        if chunks[r].shape[0]:
+            ops.append(dist.P2POp(dist.isend, chunks[r].contiguous(), r, group))
+        if n_in:
+            ops.append(dist.P2POp(dist.irecv, out[r], r, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out
+
+
+def slab_bounds(coord: torch.Tensor, world: int, quantum: float, group=None) -> List[float]:
     """world+1 increasing bounds along one axis, interior ones at point-count quantiles snapped to
-    multiples of `quantum` (the coarsest voxel size): no voxel centre of any level lies on a bound."""
-    qs = torch.quantile(coord.double().cpu()[:: max(1, coord.numel() // 2_000_000)],
-                        torch.linspace(0, 1, world + 1, dtype=torch.float64)[1:-1]) if world > 1 else coord.new_zeros(0)
+    multiples of `quantum` (the coarsest voxel size): no voxel centre of any level lies on a bound.
+    `coord` is this rank's share of the coordinates: the quantiles are taken over an equal-size sample
+    of every rank (identical bounds on all ranks)."""
+    if world <= 1:
+        return [-float("inf"), float("inf")]
+    m = 1 << 17
+    if coord.numel() > 0:
+        pick = torch.linspace(0, coord.numel() - 1, m, device=coord.device).long()
+        sample = coord.double()[pick]
+    else:
+        sample = torch.full((m,), float("nan"), dtype=torch.float64, device=coord.device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        parts = [torch.empty_like(sample) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, sample, group=group)
+        sample = torch.cat(parts)
+    sample = sample[~torch.isnan(sample)].cpu()
+    qs = torch.quantile(sample, torch.linspace(0, 1, world + 1, dtype=torch.float64)[1:-1])
     inner = [round(float(q) / quantum) * quantum for q in qs]
     for i in range(1, len(inner)):                         # strictly increasing
         inner[i] = max(inner[i], inner[i - 1] + quantum)
@@ -50,68 +115,102 @@ def owner_of(coord: torch.Tensor, bounds: List[float]) -> torch.Tensor:
     return torch.searchsorted(inner, coord.double().contiguous(), right=True)
 
 
+def route_points(coord: torch.Tensor, bounds: List[float], halo: float, arrays: List[torch.Tensor], group=None):
+    """Point all-to-all: every rank sends each of its points (rows of `arrays`) to every rank whose slab widened
+    by `halo` contains it.  Returns the list of arrays this rank receives (its slab + halo region)."""
+    world = _world(group)
+    if world == 1:
+        return list(arrays)
+    c = coord.double()
+    per_rank = []
+    for r in range(world):
+        sel = torch.nonzero((c >= bounds[r] - halo) & (c < bounds[r + 1] + halo)).reshape(-1)
+        per_rank.append(sel)
+    out = []
+    for a in arrays:
+        got = all_to_all_rows([a[sel].contiguous() for sel in per_rank], group)
+        out.append(torch.cat(got))
+    return out
+
+
 class HaloPlan:
     """Who sends which unknowns to whom.  send_idx[r]: my owned unknowns rank r needs;
     recv_idx[r]: my halo unknowns owned by rank r (same order on both sides)."""
 
     def __init__(self, send_idx, recv_idx, group=None):
         self.send_idx, self.recv_idx, self.group = send_idx, recv_idx, group
+        self.send_cat = torch.cat(send_idx) if send_idx else None
+        self.recv_cat = torch.cat(recv_idx) if recv_idx else None
+        self.send_counts = [int(i.numel()) for i in send_idx]
+        self.recv_counts = [int(i.numel()) for i in recv_idx]
+        self._bufs = None
+
+    @property
+    def bytes_per_exchange(self) -> int:
+        return 4 * (sum(self.send_counts) + sum(self.recv_counts))
 
     def exchange(self, vec: torch.Tensor):
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+        """halo entries of `vec` <- the owners' values.  CUDA: pack kernel, one all-to-all, unpack kernel."""
+        if _world(self.group) == 1:
             return vec
-        rank = dist.get_rank(self.group)
-        ops, recv_bufs = [], {}
-        for r, idx in enumerate(self.send_idx):
-            if r != rank and idx.numel():
-                ops.append(dist.P2POp(dist.isend, vec[idx].contiguous(), r, self.group))
+        if vec.is_cuda and dist.get_backend(self.group) == "nccl":
+            st = stream_ptr(vec.device)
+            if self._bufs is None:
+                self._bufs = (torch.empty(max(sum(self.send_counts), 1), dtype=torch.float32, device=vec.device),
+                              torch.empty(max(sum(self.recv_counts), 1), dtype=torch.float32, device=vec.device))
+            sbuf, rbuf = self._bufs
+            ns, nr = sum(self.send_counts), sum(self.recv_counts)
+            call("nksr_gather_f32", vec, self.send_cat, ns, sbuf, st)
+            dist.all_to_all_single(rbuf[:nr], sbuf[:ns], output_split_sizes=self.recv_counts,
+                                   input_split_sizes=self.send_counts, group=self.group)
+            call("nksr_scatter_f32", rbuf, self.recv_cat, nr, vec, st)
+            return vec
+        got = all_to_all_rows([vec[i] for i in self.send_idx], self.group)
+        rank = _rank(self.group)
         for r, idx in enumerate(self.recv_idx):
             if r != rank and idx.numel():
-                recv_bufs[r] = torch.empty(idx.numel(), dtype=vec.dtype, device=vec.device)
-                ops.append(dist.P2POp(dist.irecv, recv_bufs[r], r, self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for r, buf in recv_bufs.items():
-            vec[self.recv_idx[r]] = buf
+                vec[idx] = got[r]
         return vec
 
 
 def build_halo_plan(level_keys: List[torch.Tensor], owner: List[torch.Tensor], offsets: List[int], group=None):
     """level_keys[l]: sorted Morton keys of my local voxels; owner[l]: owning rank of each.
     Voxels are matched across ranks by (level, key) -- bit-exact keys make this an integer join."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world, rank = _world(group), _rank(group)
     dev = level_keys[0].device
-    need = [[None] * len(level_keys) for _ in range(world)]          # need[r][l] = keys I want from r
-    recv_idx = [[] for _ in range(world)]
-    for l, (keys, own) in enumerate(zip(level_keys, owner)):
-        for r in range(world):
-            if r == rank:
-                continue
-            sel = torch.nonzero(own == r).reshape(-1)
-            need[r][l] = keys[sel].cpu()
-            recv_idx[r].append(sel + offsets[l])
-    recv_idx = [torch.cat(v) if v else torch.zeros(0, dtype=torch.long, device=dev) for v in recv_idx]
+    empty = torch.zeros(0, dtype=torch.long, device=dev)
     if world == 1:
-        return HaloPlan([torch.zeros(0, dtype=torch.long, device=dev)], recv_idx, group)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, need, group=group)                # gathered[s][r][l]: keys s wants from r
+        return HaloPlan([empty], [empty], group)
+    # what I need from rank r: (level, key) of my halo voxels owned by r, as int64 rows
+    want, recv_idx = [], []
+    for r in range(world):
+        rows, idx = [], []
+        if r != rank:
+            for l, (keys, own) in enumerate(zip(level_keys, owner)):
+                sel = torch.nonzero(own == r).reshape(-1)
+                rows.append(torch.stack([torch.full_like(keys[sel], l), keys[sel]], dim=1))
+                idx.append(sel + offsets[l])
+        want.append(torch.cat(rows) if rows else torch.zeros((0, 2), dtype=torch.int64, device=dev))
+        recv_idx.append(torch.cat(idx) if idx else empty)
+    asked = all_to_all_rows(want, group)                               # asked[s]: what rank s wants from me
     send_idx = []
     for s in range(world):
-        parts = []
-        if s != rank:
-            for l, keys in enumerate(level_keys):
-                want = gathered[s][rank][l]
-                if want is None or want.numel() == 0:
-                    continue
-                want = want.to(dev)
-                pos = torch.searchsorted(keys, want).clamp(max=max(keys.numel() - 1, 0))
-                if keys.numel() == 0 or not bool((keys[pos] == want).all()):
-                    raise _lib.NksrError(f"rank {s} asks rank {rank} for voxels it does not hold on level {l}: "
-                                         "halo too thin for this hierarchy")
-                parts.append(pos + offsets[l])
-        send_idx.append(torch.cat(parts) if parts else torch.zeros(0, dtype=torch.long, device=dev))
+        req = asked[s]
+        if s == rank or req.shape[0] == 0:
+            send_idx.append(empty)
+            continue
+        parts = torch.empty(req.shape[0], dtype=torch.long, device=dev)
+        for l, keys in enumerate(level_keys):
+            m = req[:, 0] == l
+            if not bool(m.any()):
+                continue
+            k = req[m, 1]
+            pos = torch.searchsorted(keys, k).clamp(max=max(keys.numel() - 1, 0))
+            if keys.numel() == 0 or not bool((keys[pos] == k).all()):
+                raise _lib.NksrError(f"rank {s} asks rank {rank} for voxels it does not hold on level {l}: "
+                                     "halo too thin for this hierarchy")
+            parts[m] = pos + offsets[l]
+        send_idx.append(parts)
     return HaloPlan(send_idx, recv_idx, group)
 
 
@@ -122,102 +221,129 @@ def _gsum(t: torch.Tensor, group) -> torch.Tensor:
     return s
 
 
-def pcg_distributed(sysm, mask: torch.Tensor, plan: HaloPlan, tol: float, max_iter: int, check_every: int = 1,
+def pcg_distributed(sysm, owned: torch.Tensor, plan: HaloPlan, tol: float, max_iter: int, check_every: int = 16,
                     group=None):
-    """Jacobi-PCG on the rows selected by `mask` (1 = owned) of every rank's local CSR system."""
+    """Jacobi-PCG (Chronopoulos-Gear form: one fused all-reduce per iteration) on the rows every rank owns of its
+    local CSR system.  `owned`: bool per local unknown.  Returns (x with halo entries filled, info dict)."""
     n, dev = sysm.n, sysm.rhs.device
     st = stream_ptr(dev)
-    dinv = torch.where(sysm.diag > 0, 1.0 / sysm.diag.clamp(min=1e-30), torch.zeros_like(sysm.diag)) * mask
-    b = sysm.rhs * mask
-    x = torch.zeros(n, dtype=torch.float32, device=dev)
-    r = b.clone()
-    z = r * dinv
-    p = z.clone()
-    plan.exchange(p)
-    ap = torch.empty_like(p)
-    rz = _gsum(r.double() * z.double(), group)
-    bb = float(_gsum(b.double() * b.double(), group).item())
-    if not bb > 0:
-        return x, 0, 0.0
-    it, rr = 0, bb
-    while it < max_iter:
-        call("nksr_spmv", sysm.rowptr, sysm.col, sysm.val, p, ap, n, st)
-        pap = _gsum(p.double() * ap.double() * mask, group)
-        alpha = (rz / pap).float()
-        x.add_(p * alpha * mask)
-        r.sub_(ap * alpha * mask)
-        z = r * dinv
-        rz_new = _gsum(r.double() * z.double(), group)
-        beta = (rz_new / rz).float()
-        rz = rz_new
-        p = z + beta * p * mask
-        plan.exchange(p)
-        it += 1
-        if it % check_every == 0 or it == max_iter:
-            rr = float(_gsum(r.double() * r.double(), group).item())
-            if not rr == rr or rr <= tol * tol * bb:
-                break
+    world = _world(group)
+    own8 = owned.to(torch.uint8).contiguous()
+    x, r, u, w, p, s = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(6))
+    nb = call("nksr_dcg_workspace_bytes")
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    red = torch.zeros(3, dtype=torch.float64, device=dev)
+    info = (C.c_double * 4)()
+    call("nksr_dcg_init", sysm.diag, sysm.rhs, own8, x, r, u, p, s, n, ws, nb, red, st)
+    if world > 1:
+        dist.all_reduce(red, group=group)
+    call("nksr_dcg_begin", ws, red, float(tol), int(max_iter), st)
+    launched, allreduces, exchanges = 0, 1 if world > 1 else 0, 0
+    while True:
+        for _ in range(max(int(check_every), 1)):
+            plan.exchange(u)
+            call("nksr_dcg_spmv_dots", sysm.rowptr, sysm.col, sysm.val, own8, r, u, w, n, ws, red, st)
+            if world > 1:
+                dist.all_reduce(red, group=group)
+                allreduces += 1
+                exchanges += 1
+            call("nksr_dcg_update", sysm.diag, own8, x, r, u, w, p, s, n, ws, red, st)
+            launched += 1
+        call("nksr_dcg_status", ws, info, st)
+        if info[3] != 0 or launched > max_iter + check_every:
+            break
     plan.exchange(x)                                           # halo coefficients for evaluation / meshing
-    return x, it, (rr / bb) ** 0.5
+    return x, {"iterations": int(info[0]), "relative_residual": float(info[1]), "converged": int(info[2]) == 0,
+               "allreduces": allreduces, "halo_exchanges": exchanges + (1 if world > 1 else 0),
+               "iterations_launched": launched}
 
 
-def reconstruct_global(reconstructor, xyz: torch.Tensor, normal: torch.Tensor, voxel_size: float,
+def reconstruct_global(reconstructor, xyz: torch.Tensor, normal: Optional[torch.Tensor], voxel_size: float,
                        halo_voxels: int = 8, axis: Optional[int] = None, approx_kernel_grad: bool = False,
-                       solver_tol: float = 1e-5, solver_max_iter: int = 2000, group=None):
-    """All ranks hold the same oriented cloud; each reconstructs and owns one slab of ONE global
-    system.  Returns a KernelField over this rank's slab+halo region with attributes
+                       solver_tol: float = 1e-5, solver_max_iter: int = 2000, group=None, sensor=None,
+                       preprocess_fn=None, distributed_input: bool = False):
+    """ONE global system over all ranks.  `distributed_input=False`: every rank passes the same whole cloud
+    (each keeps its slab + halo); True: every rank passes ITS SHARE of the cloud and the points are routed to
+    the ranks that need them by one all-to-all.  Returns a KernelField over this rank's slab+halo region with
     `.owned` (per-unknown bool), `.owned_cells` (level-0 mask for meshing) and `.solve_info`."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world, rank = _world(group), _rank(group)
     dev = reconstructor.device
     xyz = xyz.detach().to(dev, torch.float32).contiguous()
-    normal = normal.detach().to(dev, torch.float32).contiguous()
+    normal = normal.detach().to(dev, torch.float32).contiguous() if normal is not None else None
+    sensor = sensor.detach().to(dev, torch.float32).contiguous() if sensor is not None else None
     L = reconstructor.tree_depth
     w_top = float(voxel_size) * (2 ** (L - 1))
+    lo_hi = torch.stack([xyz.min(dim=0).values, -xyz.max(dim=0).values]) if xyz.shape[0] else \
+        torch.full((2, 3), float("inf"), device=dev)
+    if world > 1:
+        dist.all_reduce(lo_hi, op=dist.ReduceOp.MIN, group=group)
     if axis is None:
-        axis = int(torch.argmax(xyz.max(dim=0).values - xyz.min(dim=0).values).item())
-    bounds = slab_bounds(xyz[:, axis], world, w_top)
+        axis = int(torch.argmax(-lo_hi[1] - lo_hi[0]).item())
+    bounds = slab_bounds(xyz[:, axis], world, w_top, group) if world > 1 else \
+        [-float("inf"), float("inf")]
+    if world > 1 and not distributed_input:                    # same cloud everywhere -> same bounds; make sure
+        b = torch.tensor(bounds[1:-1], dtype=torch.float64, device=dev)
+        dist.broadcast(b, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        bounds = [-float("inf")] + b.tolist() + [float("inf")]
     lo, hi = bounds[rank], bounds[rank + 1]
     H = halo_voxels * w_top
-    c = xyz[:, axis]
-    local = (c >= lo - H) & (c < hi + H)
-    lx, ln = xyz[local].contiguous(), normal[local].contiguous()
-    n_points_global = int(xyz.shape[0])                                   # every rank sees the whole cloud
+    extras = [t for t in (normal, sensor) if t is not None]
+    if distributed_input:
+        routed = route_points(xyz[:, axis], bounds, H, [xyz] + extras, group)
+    else:
+        c = xyz[:, axis]
+        local = (c >= lo - H) & (c < hi + H)
+        routed = [t[local].contiguous() for t in [xyz] + extras]
+    lx = routed[0].contiguous()
+    ln = routed[1].contiguous() if normal is not None else None
+    lsens = routed[-1].contiguous() if sensor is not None else None
+    if preprocess_fn is not None:
+        lx, ln, lsens = preprocess_fn(lx, ln, lsens)
+        lx = lx.contiguous()
+    if ln is not None:
+        feat = ln
+    elif lsens is not None:
+        view = lsens - lx
+        feat = view / (torch.linalg.norm(view, dim=-1, keepdim=True) + 1e-6)
+    else:
+        raise ValueError("either normal or sensor (with a normal-estimating preprocess_fn) is required")
+    inside = (lx[:, axis].double() >= lo) & (lx[:, axis].double() < hi)
+    counts = torch.tensor([float(inside.sum().item()), 0.0], dtype=torch.float64, device=dev)
 
     svh = SparseFeatureHierarchy(voxel_size, L, dev).build_point_splatting(lx)
     net = reconstructor.network
-    enc = net.encoder(lx, ln, svh, 0)
+    enc = net.encoder(lx, feat, svh, 0)
     feats, dec_svh, _ = net.unet(enc, svh, adaptive_depth=reconstructor.adaptive_depth)
     field = KernelField(dec_svh, net.interpolators, feats.basis_features, approx_kernel_grad)
     ad = min(reconstructor.adaptive_depth, L)
-    offs = svh.offsets
+    offs = dec_svh.offsets
     # ownership of every unknown / normal location by voxel-centre coordinate (exact: integer ijk)
     owner, centres = [], []
     for l in range(L):
-        g = SparseIndexGrid(svh, l)
+        g = SparseIndexGrid(dec_svh, l)
         ijk = g.active_grid_coords()
         cen = (ijk[:, axis].double() + 0.5) * (float(voxel_size) * (2 ** l))
         owner.append(owner_of(cen, bounds))
         centres.append(g.grid_to_world(ijk))
     owned = torch.cat([o == rank for o in owner])
-    k_global = torch.tensor([float(sum(int((owner[d] == rank).sum().item()) for d in range(ad)))], device=dev,
-                            dtype=torch.float64)
+    counts[1] = float(sum(int((owner[d] == rank).sum().item()) for d in range(ad)))
     if world > 1:
-        dist.all_reduce(k_global, group=group)
-    k_global = float(k_global.item())
+        dist.all_reduce(counts, group=group)
+    n_points_global, k_global = float(counts[0].item()), float(counts[1].item())
     normal_xyz = torch.cat([centres[d] for d in range(ad)])
     normal_value = torch.cat([feats.normal_features[d] for d in range(ad)])
     from .reconstructor import NORMAL_WEIGHT, POS_WEIGHT
     sysm = field.assemble(lx, normal_xyz, -normal_value, POS_WEIGHT / n_points_global,
                           NORMAL_WEIGHT / k_global * (float(voxel_size) ** 2), 1.0)
-    plan = build_halo_plan(svh.keys, owner, offs, group)
-    alpha, iters, relres = pcg_distributed(sysm, owned.float(), plan, solver_tol, solver_max_iter, 1, group)
+    plan = build_halo_plan(dec_svh.keys, owner, offs, group)
+    alpha, info = pcg_distributed(sysm, owned, plan, solver_tol, solver_max_iter, 16, group)
     field.alpha = alpha
     field.owned = owned
     field.owned_cells = owner[0] == rank
-    field.solve_info = {"iterations": iters, "relative_residual": relres, "n": sysm.n, "nnz": sysm.nnz,
-                        "n_owned": int(owned.sum().item()), "halo_recv": int(sum(i.numel() for i in plan.recv_idx)),
-                        "slab": (lo, hi), "axis": axis}
+    field.solve_info = dict(info, n=sysm.n, nnz=sysm.nnz, n_owned=int(owned.sum().item()),
+                            halo_recv=int(sum(plan.recv_counts)), halo_send=int(sum(plan.send_counts)),
+                            halo_bytes_per_exchange=plan.bytes_per_exchange, slab=(lo, hi), axis=axis,
+                            points_local=int(lx.shape[0]), points_global=int(n_points_global))
     field.set_mask_field(LayerField(dec_svh, ad))
     return field
 

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import warnings
 from types import SimpleNamespace
 from typing import Optional
 
@@ -91,7 +92,8 @@ class KernelField(BaseField):
                  approx_kernel_grad: bool = False):
         super().__init__(svh)
         self.approx_kernel_grad = bool(approx_kernel_grad)
-        self.solver_config = {"verbose": False, "tol": 1.0e-5, "max_iter": 2000, "check_every": 10}
+        # check_every = iterations per CUDA-graph launch (one host read-back of the device-side verdict each)
+        self.solver_config = {"verbose": False, "tol": 1.0e-5, "max_iter": 2000, "check_every": 32}
         self.interpolator = interpolator
         self.alpha: Optional[torch.Tensor] = None
         self.solve_info = {}
@@ -173,14 +175,22 @@ class KernelField(BaseField):
         alpha = torch.empty(n, dtype=torch.float32, device=dev)
         nb = call("nksr_pcg_workspace_bytes", n)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-        info = (C.c_double * 4)()
+        info = (C.c_double * 8)()
         profile = int(bool(self.solver_config.get("profile")))
         call("nksr_pcg_solve", sysm.rowptr, sysm.col, sysm.val, sysm.diag, sysm.rhs, alpha, n,
              float(self.solver_config["tol"]), int(self.solver_config["max_iter"]),
              int(self.solver_config["check_every"]), profile, ws, nb, info, stream_ptr(dev))
         tm.mark("pcg")
         self.alpha = alpha
-        self.solve_info = {"iterations": int(info[0]), "relative_residual": float(info[1]), "n": n, "nnz": sysm.nnz}
+        status = int(info[4])                       # 0 converged, 1 max_iter reached, 2 NaN / breakdown
+        self.solve_info = {"iterations": int(info[0]), "relative_residual": float(info[1]), "n": n, "nnz": sysm.nnz,
+                           "converged": status == 0}
+        if status == 2:
+            raise _lib.NksrError(f"PCG broke down (non-finite residual) after {int(info[0])} iterations: the system "
+                                 "is not positive definite or the inputs are not finite")
+        if status == 1 and int(self.solver_config["max_iter"]) > 0:
+            warnings.warn(f"nksr_b200 PCG stopped at max_iter={int(self.solver_config['max_iter'])} with relative "
+                          f"residual {float(info[1]):.3e} > tol={float(self.solver_config['tol']):.1e}", RuntimeWarning)
         if profile:
             self.solve_info.update(spmv_ms=float(info[2]), spmv_launches=int(info[3]))
         if self.solver_config.get("verbose"):

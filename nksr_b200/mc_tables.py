@@ -12,7 +12,7 @@ watertight wherever cells exist.  Segments are chained into closed loops and fan
 with the orientation that makes triangle normals point from inside to outside.
 
 `tools/gen_mc_tables.py` writes these tables to `nksr_b200/csrc/mc_tables.inc` for the CUDA
-kernels; `tests/test_mc_tables.py` checks the committed .inc against this generator.
+kernels; `tests/test_cpu_oracle.py` checks the committed .inc against this generator.
 """
 from __future__ import annotations
 

@@ -198,8 +198,6 @@ class Reconstructor:
         tm.mark("network")
         field.solver_config["tol"] = float(solver_tol)
         field.solver_config["max_iter"] = int(solver_max_iter)
-        # large systems: an iteration costs milliseconds, so test convergence every iteration
-        field.solver_config["check_every"] = 1 if dec_svh.num_unknowns > 1_000_000 else 10
         ad = min(self.adaptive_depth, dec_svh.depth)
         normal_xyz = torch.cat([dec_svh.get_voxel_centers(d) for d in range(ad)])
         normal_value = torch.cat([feats.normal_features[d] for d in range(ad)])
@@ -207,6 +205,7 @@ class Reconstructor:
         field.solve(xyz, normal_xyz, -normal_value, POS_WEIGHT / xyz.shape[0], normal_weight, 1.0,
                     fused_mode=fused_mode)
         field.set_mask_field(LayerField(dec_svh, ad))
+        field._n_normal = int(normal_xyz.shape[0])
         return field
 
     def reconstruct(self, xyz: torch.Tensor, normal: Optional[torch.Tensor] = None,
@@ -233,8 +232,12 @@ class Reconstructor:
         field = self._reconstruct_one(xyz, normal, sensor, float(voxel_size), approx_kernel_grad, solver_tol,
                                       fused_mode, solver_max_iter)
         self.last_stats = dict(field.solve_info, voxel_size=float(voxel_size), points=int(xyz.shape[0]),
-                               stages_ms=self._timer.report())
+                               normal_locations=int(getattr(field, "_n_normal", 0)))
         return field
+
+    def stage_times(self) -> dict:
+        """CUDA-event time per stage (ms) of the last `reconstruct` call when NKSR_STAGE_TIMES=1 (synchronises)."""
+        return self._timer.report()
 
     def _reconstruct_chunks(self, xyz, normal, sensor, voxel_size, chunk_size, preprocess_fn, approx_kernel_grad,
                             solver_tol, fused_mode, solver_max_iter, chunk_filter=None):

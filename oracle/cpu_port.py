@@ -44,6 +44,14 @@ def lib():
         L.nksr_cpu_pcg.restype = C.c_int
         L.nksr_cpu_pcg.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.nksr_cpu_threads.restype = C.c_int
+        L.nksr_cpu_evaluate.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.nksr_cpu_svh_from_keys.restype = C.c_void_p
+        L.nksr_cpu_svh_from_keys.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_float, C.c_int]
+        L.nksr_cpu_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.nksr_cpu_structural_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.nksr_cpu_structural_row.restype = C.c_int64
+        L.nksr_cpu_structural_row.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -53,10 +61,49 @@ def _p(a):
 
 
 class CpuSvh:
-    def __init__(self, xyz: np.ndarray, voxel_size: float, depth: int):
-        self.xyz = np.ascontiguousarray(xyz, np.float32)
+    def __init__(self, xyz: np.ndarray, voxel_size: float, depth: int, keys=None):
         self.depth = depth
+        self.voxel_size = float(np.float32(voxel_size))
+        if keys is not None:                       # adopt sorted unique keys per level (pruned hierarchies)
+            ks = [np.ascontiguousarray(k, np.int64) for k in keys]
+            ptrs = (C.c_void_p * depth)(*[k.ctypes.data for k in ks])
+            cnt = np.array([k.shape[0] for k in ks], np.int64)
+            self.h = lib().nksr_cpu_svh_from_keys(ptrs, _p(cnt), np.float32(voxel_size), depth)
+            return
+        self.xyz = np.ascontiguousarray(xyz, np.float32)
         self.h = lib().nksr_cpu_svh_build(_p(self.xyz), self.xyz.shape[0], np.float32(voxel_size), depth)
+
+    def offsets(self):
+        return np.concatenate([[0], np.cumsum([self.n(l) for l in range(self.depth)])]).astype(np.int64)
+
+    def locate(self, xyz):
+        q = np.ascontiguousarray(xyz, np.float32)
+        out = np.empty((self.depth, q.shape[0]), np.int32)
+        lib().nksr_cpu_locate(self.h, _p(q), q.shape[0], _p(out))
+        return out
+
+    def structural_counts(self):
+        """stored entries per row of the SPEC S6 pattern (own + transposed)."""
+        out = np.empty(int(self.offsets()[-1]), np.int32)
+        lib().nksr_cpu_structural_counts(self.h, _p(out))
+        return out
+
+    def structural_row(self, row, capacity):
+        buf = np.empty(int(capacity), np.int32)
+        m = lib().nksr_cpu_structural_row(self.h, int(row), _p(buf))
+        return buf[:m].copy()
+
+    def evaluate(self, feats, alpha, xyz, grad=False, approx=False):
+        """f (M,) [and grad (M,3)] in float64 at the queries (SPEC S3/S4)."""
+        feats = [np.ascontiguousarray(f, np.float32) for f in feats]
+        ptrs = (C.c_void_p * len(feats))(*[f.ctypes.data for f in feats])
+        q = np.ascontiguousarray(xyz, np.float32)
+        a = np.ascontiguousarray(alpha, np.float32)
+        f = np.empty(q.shape[0], np.float64)
+        g = np.empty((q.shape[0], 3), np.float64) if grad else None
+        lib().nksr_cpu_evaluate(self.h, ptrs, feats[0].shape[1], _p(a), _p(q), q.shape[0], int(grad), int(approx),
+                                _p(f), _p(g) if grad else None)
+        return (f, g) if grad else f
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -229,19 +229,27 @@ void* nksr_cpu_build_system(void* h, const float* const* feat, int C, const floa
                        &E[r0 + 2 * (size_t)maxrow + len]);
     Elen[n_pos + 3 * k] = Elen[n_pos + 3 * k + 1] = Elen[n_pos + 3 * k + 2] = len;
   }
-  // transpose index: for every unknown the (row, value) pairs touching it
+  // transpose index: for every unknown the (row, value) pairs touching it (built in parallel; the order of the
+  // pairs inside one unknown's list is scheduling dependent, the fp64 accumulation below makes that immaterial)
   std::vector<int64_t> tptr(n + 1, 0);
+#pragma omp parallel for schedule(static)
   for (int64_t r = 0; r < M; ++r)
-    for (int e = 0; e < Elen[r]; ++e) ++tptr[E[(size_t)r * maxrow + e].col + 1];
+    for (int e = 0; e < Elen[r]; ++e) {
+#pragma omp atomic
+      ++tptr[E[(size_t)r * maxrow + e].col + 1];
+    }
   for (int64_t i = 0; i < n; ++i) tptr[i + 1] += tptr[i];
   std::vector<int64_t> trow(tptr[n]);
   std::vector<float> tval(tptr[n]);
   {
     std::vector<int64_t> cur(tptr.begin(), tptr.end() - 1);
+#pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < M; ++r)
       for (int e = 0; e < Elen[r]; ++e) {
         const Entry& en = E[(size_t)r * maxrow + e];
-        const int64_t p = cur[en.col]++;
+        int64_t p;
+#pragma omp atomic capture
+        p = cur[en.col]++;
         trow[p] = r;
         tval[p] = en.val;
       }
@@ -373,6 +381,143 @@ int nksr_cpu_pcg(void* h, float tol, int max_iter, float* x, double* relres) {
   }
   *relres = std::sqrt(rr / bb);
   return it;
+}
+
+
+// f(x) = sum_l sum_{i in N27(b_l(x))} alpha_i K_l(x,i) and (optionally) its gradient (SPEC S3/S4), fp64 sums.
+// Call site restated: field.evaluate_f(xyz, grad) (models/loss.py:189-198,225).
+void nksr_cpu_evaluate(void* h, const float* const* feat, int C, const float* alpha, const float* xyz, int64_t m,
+                       int want_grad, int approx, double* f, double* g) {
+  const Svh& s = *static_cast<Svh*>(h);
+  const int L = s.depth;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t q = 0; q < m; ++q) {
+    Entry v[27], gx[27], gy[27], gz[27];
+    double acc = 0, ax = 0, ay = 0, az = 0;
+    for (int l = 0; l < L; ++l) {
+      const int c = level_row(s, l, feat, C, xyz + 3 * q, false, false, v, nullptr, nullptr, nullptr);
+      for (int e = 0; e < c; ++e) acc += (double)alpha[v[e].col] * v[e].val;
+      if (want_grad) {
+        const int cg = level_row(s, l, feat, C, xyz + 3 * q, true, approx != 0, nullptr, gx, gy, gz);
+        for (int e = 0; e < cg; ++e) {
+          const double a = alpha[gx[e].col];
+          ax += a * gx[e].val; ay += a * gy[e].val; az += a * gz[e].val;
+        }
+      }
+    }
+    f[q] = acc;
+    if (want_grad) { g[3 * q] = ax; g[3 * q + 1] = ay; g[3 * q + 2] = az; }
+  }
+}
+
+// hierarchy from given (sorted, unique) keys per level -- for pruned / adaptive hierarchies
+void* nksr_cpu_svh_from_keys(const int64_t* const* keys, const int64_t* counts, float voxel_size, int depth) {
+  Svh* s = new Svh();
+  s->w = voxel_size;
+  s->depth = depth;
+  s->offset.assign(depth + 1, 0);
+  for (int l = 0; l < depth; ++l) {
+    s->keys[l].assign(keys[l], keys[l] + counts[l]);
+    s->offset[l + 1] = s->offset[l] + counts[l];
+  }
+  return s;
+}
+
+// containing voxel index per level (-1 when inactive), (L, m) row-major
+void nksr_cpu_locate(void* h, const float* xyz, int64_t m, int32_t* base) {
+  const Svh& s = *static_cast<Svh*>(h);
+  const float half_w = s.w * 0.5f;
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < m; ++q) {
+    int hh[3];
+    half_coords(xyz + 3 * q, half_w, hh);
+    for (int l = 0; l < s.depth; ++l)
+      base[(int64_t)l * m + q] = s.find(l, morton3(hh[0] >> (l + 1), hh[1] >> (l + 1), hh[2] >> (l + 1)));
+  }
+}
+
+// SPEC S6 storage pattern, restated independently of the numpy oracle: row (l,i) stores every ACTIVE column in
+// the same-level 5^3 stencil, in the box [((u-1)>>k)-1, ((u+1)>>k)+1]^3 of every coarser level l+k, and the
+// transposes of the latter.  cnt[row] = stored entries of the row (own + transposed).
+void nksr_cpu_structural_counts(void* h, int32_t* cnt) {
+  const Svh& s = *static_cast<Svh*>(h);
+  const int L = s.depth;
+  const int64_t n = s.total();
+  for (int64_t i = 0; i < n; ++i) cnt[i] = 0;
+  for (int l = 0; l < L; ++l) {
+    const int64_t nl = (int64_t)s.keys[l].size();
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < nl; ++i) {
+      int x, y, z;
+      demorton3(s.keys[l][i], x, y, z);
+      int own = 0;
+      for (int dx = -2; dx <= 2; ++dx)
+        for (int dy = -2; dy <= 2; ++dy)
+          for (int dz = -2; dz <= 2; ++dz)
+            if (s.find(l, morton3(x + dx, y + dy, z + dz)) >= 0) ++own;
+      for (int k = 1; l + k < L; ++k) {
+        const int lo[3] = {((x - 1) >> k) - 1, ((y - 1) >> k) - 1, ((z - 1) >> k) - 1};
+        const int hi[3] = {((x + 1) >> k) + 1, ((y + 1) >> k) + 1, ((z + 1) >> k) + 1};
+        for (int cx = lo[0]; cx <= hi[0]; ++cx)
+          for (int cy = lo[1]; cy <= hi[1]; ++cy)
+            for (int cz = lo[2]; cz <= hi[2]; ++cz) {
+              const int c = s.find(l + k, morton3(cx, cy, cz));
+              if (c < 0) continue;
+              ++own;
+#pragma omp atomic
+              ++cnt[s.offset[l + k] + c];
+            }
+      }
+#pragma omp atomic
+      cnt[s.offset[l] + i] += own;
+    }
+  }
+}
+
+// sorted global column indices of one row of the SPEC S6 pattern; returns their number (cols holds >= cnt[row])
+int64_t nksr_cpu_structural_row(void* h, int64_t row, int32_t* cols) {
+  const Svh& s = *static_cast<Svh*>(h);
+  const int L = s.depth;
+  int l = 0;
+  while (l + 1 < L && row >= s.offset[l + 1]) ++l;
+  const int64_t i = row - s.offset[l];
+  int x, y, z;
+  demorton3(s.keys[l][i], x, y, z);
+  std::vector<int32_t> out;
+  for (int dx = -2; dx <= 2; ++dx)
+    for (int dy = -2; dy <= 2; ++dy)
+      for (int dz = -2; dz <= 2; ++dz) {
+        const int j = s.find(l, morton3(x + dx, y + dy, z + dz));
+        if (j >= 0) out.push_back((int32_t)(s.offset[l] + j));
+      }
+  for (int k = 1; l + k < L; ++k)
+    for (int cx = ((x - 1) >> k) - 1; cx <= ((x + 1) >> k) + 1; ++cx)
+      for (int cy = ((y - 1) >> k) - 1; cy <= ((y + 1) >> k) + 1; ++cy)
+        for (int cz = ((z - 1) >> k) - 1; cz <= ((z + 1) >> k) + 1; ++cz) {
+          const int c = s.find(l + k, morton3(cx, cy, cz));
+          if (c >= 0) out.push_back((int32_t)(s.offset[l + k] + c));
+        }
+  // transposes: finer voxels j (level l-k) whose box on this level contains (x,y,z): j's coords u satisfy
+  // ((u-1)>>k)-1 <= x <= ((u+1)>>k)+1  <=>  u in [((x-1)<<k) - 1, ((x+2)<<k)] per axis (checked exactly below)
+  for (int k = 1; l - k >= 0; ++k) {
+    const int lf = l - k;
+    const int span = 1 << k;
+    for (int ux = ((x - 2) << k); ux < ((x + 3) << k); ++ux) {
+      if (!(((ux - 1) >> k) - 1 <= x && x <= ((ux + 1) >> k) + 1)) continue;
+      for (int uy = ((y - 2) << k); uy < ((y + 3) << k); ++uy) {
+        if (!(((uy - 1) >> k) - 1 <= y && y <= ((uy + 1) >> k) + 1)) continue;
+        for (int uz = ((z - 2) << k); uz < ((z + 3) << k); ++uz) {
+          if (!(((uz - 1) >> k) - 1 <= z && z <= ((uz + 1) >> k) + 1)) continue;
+          const int j = s.find(lf, morton3(ux, uy, uz));
+          if (j >= 0) out.push_back((int32_t)(s.offset[lf] + j));
+        }
+      }
+    }
+    (void)span;
+  }
+  std::sort(out.begin(), out.end());
+  std::memcpy(cols, out.data(), out.size() * sizeof(int32_t));
+  return (int64_t)out.size();
 }
 
 int nksr_cpu_threads(void) {

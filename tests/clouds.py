@@ -37,3 +37,31 @@ def offset_blob(n, seed=5, scale=3.0, shift=(-17.3, 41.9, -5.25)):
     p = rng.normal(size=(n, 3)); p /= np.linalg.norm(p, axis=1, keepdims=True)
     r = 1.0 + 0.2 * np.sin(3 * p[:, 0]) * np.cos(2 * p[:, 1])
     return (p * r[:, None] * scale + np.asarray(shift)).astype(np.float32), p.astype(np.float32)
+
+
+def read_ply_xyz_normal(path):
+    """minimal reader for binary little-endian PLY files whose vertex element starts with float32
+    x y z nx ny nz (the layout of the reference's assets/bunny.ply, examples/common.py:19-22)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    header = raw[:end].decode("ascii").splitlines()
+    assert "format binary_little_endian 1.0" in header
+    n = next(int(l.split()[2]) for l in header if l.startswith("element vertex"))
+    props = []
+    for l in header[header.index(next(h for h in header if h.startswith("element vertex"))) + 1:]:
+        if not l.startswith("property"):
+            break
+        props.append(l.split())
+    assert [p[2] for p in props[:6]] == ["x", "y", "z", "nx", "ny", "nz"] and all(p[1] == "float" for p in props[:6])
+    size = {"float": 4, "uchar": 1, "double": 8, "int": 4, "uint": 4}
+    stride = sum(size[p[1]] for p in props)
+    body = np.frombuffer(raw, dtype=np.uint8, count=n * stride, offset=end).reshape(n, stride)
+    v = body[:, :24].copy().view(np.float32).reshape(n, 6)
+    return np.ascontiguousarray(v[:, :3]), np.ascontiguousarray(v[:, 3:6])
+
+
+def bunny():
+    """BASELINE.json configs[0]: assets/bunny.ply as shipped by the reference (10 000 oriented points)."""
+    import os
+    return read_ply_xyz_normal(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bunny.ply"))

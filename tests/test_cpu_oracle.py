@@ -164,7 +164,8 @@ def test_ctypes_signatures_match_the_header_prototypes():
         for p, k in zip(plist, kinds):
             if "*" in p:
                 base = re.sub(r"\bconst\b", "", p).split("*")[0].strip()
-                want = struct.get(base, "d" if base == "double" else "p")
+                # double*: `info` is a HOST array (ctypes double array), every other one a device buffer
+                want = struct.get(base, "d" if (base == "double" and p.split("*")[-1].strip() == "info") else "p")
                 assert k == want, (name, p, k)
             else:
                 assert k == scalar[p.split()[-2] if len(p.split()) > 1 else p], (name, p, k)

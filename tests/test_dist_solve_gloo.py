@@ -45,6 +45,20 @@ def _worker(rank, world, port, out):
         got = [None] * world
         dist.all_gather_object(got, b)
         assert got[0] == got[1]
+        # point all-to-all: every rank starts with a different share of one cloud and ends with its slab + halo
+        g = torch.Generator().manual_seed(7)
+        cloud = torch.rand(4000, 3, generator=g) * 100.0
+        extra = torch.arange(4000, dtype=torch.float32)[:, None].repeat(1, 3)
+        mine = slice(0, 1500) if rank == 0 else slice(1500, 4000)          # unequal shares
+        px, pe = ds.route_points(cloud[mine, 0], bounds, 10.0, [cloud[mine], extra[mine]])
+        lo_, hi_ = (-1e30, 60.0) if rank == 0 else (40.0, 1e30)
+        want = (cloud[:, 0] >= lo_) & (cloud[:, 0] < hi_)
+        assert px.shape[0] == int(want.sum()) and torch.equal(torch.sort(pe[:, 0]).values, extra[want, 0])
+        assert torch.equal(cloud[pe[:, 0].long()], px)                      # rows stay together
+        b2 = ds.slab_bounds(cloud[mine, 0], 2, 5.0)                         # bounds from distributed samples agree
+        got = [None] * world
+        dist.all_gather_object(got, b2)
+        assert got[0] == got[1] and 40.0 <= b2[1] <= 60.0
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback

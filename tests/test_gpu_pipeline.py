@@ -1,0 +1,98 @@
+"""Whole-pipeline parity: BASELINE.json configs[0] -- the reference's own asset
+assets/bunny.ply run the way examples/recons_simple.py:20-27 runs it (detail_level=1.0, extract_dual_mesh(mise_iter=1))
+-- through the CUDA path and through the CPU restatement (oracle/pipeline.py), compared as FIELDS and as SURFACES.
+Unlike tests/test_gpu_parity.py::test_dual_mesh_matches_oracle (which feeds the oracle's MC driver the GPU field values to
+pin the MC bookkeeping exactly), the oracle mesh here comes from the oracle's own evaluator on the oracle's own
+coefficients, so the whole chain is compared end to end."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+from scipy.spatial import cKDTree
+
+from oracle import nksr_oracle as O
+from oracle import pipeline
+from tests import clouds
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _oracle_mesh(ref, adaptive_depth, mise):
+    osvh, svh = ref["osvh"], ref["svh"]
+
+    def mask(v):                                 # LayerField(svh, adaptive_depth), models/nksr_net.py:132
+        b = svh.locate(v.astype(np.float32))
+        return (b[:adaptive_depth] >= 0).any(axis=0)
+    return O.extract_dual_mesh(osvh, lambda q: svh.evaluate(ref["feats"], ref["alpha"], q), 1, mise, mask)
+
+
+def _surface_distance(va, vb):
+    d1 = cKDTree(vb).query(va)[0]
+    d2 = cKDTree(va).query(vb)[0]
+    return d1, d2
+
+
+def test_cfg1_bunny_field_and_mesh_match_oracle(cuda):
+    import nksr_b200
+    xyz, nrm = clouds.bunny()
+    assert xyz.shape == (10000, 3)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    rec = nksr_b200.Reconstructor(cuda)
+    field = rec.reconstruct(t(xyz), t(nrm), detail_level=1.0, solver_tol=1e-6)        # examples/recons_simple.py:26
+    W = rec.last_stats["voxel_size"]
+    mesh = field.extract_dual_mesh(mise_iter=1)                                        # examples/recons_simple.py:27
+    ref = pipeline.reconstruct(xyz, normal=nrm, voxel_size=W, depth=4, adaptive_depth=2,
+                               network=copy.deepcopy(rec.network).cpu(), solver_tol=1e-8)
+    for l in range(4):
+        assert np.array_equal(_np(field.svh.keys[l]), ref["svh"].keys(l))
+    # field
+    rng = np.random.default_rng(0)
+    q = np.concatenate([xyz[:3000], xyz[:3000] + rng.normal(size=(3000, 3)).astype(np.float32) * np.float32(W)])
+    r = field.evaluate_f(t(q), grad=True)
+    fo, go = ref["svh"].evaluate(ref["feats"], ref["alpha"], q, grad=True)
+    fs = np.abs(fo).max()
+    assert np.abs(_np(r.value) - fo).max() <= 5e-3 * fs
+    assert np.abs(_np(r.gradient) - go).max() <= 2e-2 * np.abs(go).max()
+    # surface: same mesh up to the cells whose corner values sit within rounding of zero
+    vo, fo_ = _oracle_mesh(ref, 2, 1)
+    v = _np(mesh.v).astype(np.float64)
+    assert abs(mesh.f.shape[0] - fo_.shape[0]) <= 0.01 * fo_.shape[0] + 8
+    d1, d2 = _surface_distance(v, vo.astype(np.float64))
+    cell = W / 2                                                 # final cell size after one MISE round
+    assert np.quantile(d1, 0.99) <= 0.02 * cell and np.quantile(d2, 0.99) <= 0.02 * cell
+    assert max(d1.max(), d2.max()) <= 1.8 * cell                 # differing cells stay within a cell diagonal
+    # manifold: no edge of the (mask-trimmed, hence open at the band boundary) mesh is shared by more than two faces
+    f = _np(mesh.f)
+    e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert cnt.max() <= 2 and (cnt == 2).mean() > 0.8
+
+
+def test_mesh_of_solved_field_matches_oracle_mesh_as_surface(cuda):
+    """a7 end to end on the noisy-sphere setup of the parity tests: GPU mesh of the GPU solution against the oracle's
+    mesh of the oracle's solution, for mise_iter = 0, 1, 2 and grid_upsample = 2."""
+    import nksr_b200
+    xyz, nrm = clouds.sphere(4000, noise=0.002)
+    W, L = 0.05, 3
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    rec = nksr_b200.Reconstructor(cuda, tree_depth=L)
+    field = rec.reconstruct(t(xyz), t(nrm), voxel_size=W, solver_tol=1e-7)
+    ref = pipeline.reconstruct(xyz, normal=nrm, voxel_size=W, depth=L, adaptive_depth=2,
+                               network=copy.deepcopy(rec.network).cpu(), solver_tol=1e-9)
+    osvh, svh = ref["osvh"], ref["svh"]
+    mask = lambda v: (svh.locate(v.astype(np.float32))[:2] >= 0).any(axis=0)
+    ev = lambda q: svh.evaluate(ref["feats"], ref["alpha"], q)
+    for g, mise in ((1, 0), (1, 1), (1, 2), (2, 1)):
+        mesh = field.extract_dual_mesh(grid_upsample=g, mise_iter=mise)
+        vo, fo = O.extract_dual_mesh(osvh, ev, g, mise, mask)
+        cell = W / (g * 2 ** mise)
+        assert abs(mesh.f.shape[0] - fo.shape[0]) <= 0.01 * fo.shape[0] + 8, (g, mise)
+        d1, d2 = _surface_distance(_np(mesh.v).astype(np.float64), vo.astype(np.float64))
+        assert np.quantile(d1, 0.99) <= 0.02 * cell and np.quantile(d2, 0.99) <= 0.02 * cell, (g, mise)
+        r = np.linalg.norm(_np(mesh.v), axis=1)
+        assert abs(np.median(r) - 0.35) < 0.004
