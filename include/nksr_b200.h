@@ -167,6 +167,17 @@ NKSR_API int nksr_gram_fill_placed(const nksr_svh_t* svh, const nksr_feat_t* fea
                           const int32_t* cnt, const int64_t* rowptr, const nksr_placement_t* placement,
                           int32_t* col, float* val, float* rhs, float* diag, void* stream);
 
+/* the same fill with the sibling-group decomposition (one warp per level-(l+1) voxel = up to eight matrix rows
+ * that share their constraint rows, column tables and flush indices): same CSR, same order.  Needs depth <= 4
+ * and the virtual level above the coarsest one (svh->parent[depth-1], child8[depth], nbr27[depth]); returns
+ * NKSR_E_INVALID otherwise (callers then use nksr_gram_fill_placed). */
+NKSR_API int nksr_gram_fill_grouped(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_constraints_t* c,
+                           const int32_t* cnt, const int64_t* rowptr, const nksr_placement_t* placement,
+                           int32_t* col, float* val, float* rhs, float* diag, void* stream);
+
+/* nksr_gram_count_own with one column table per sibling group (same restrictions as nksr_gram_fill_grouped) */
+NKSR_API int nksr_gram_count_grouped(const nksr_svh_t* svh, int32_t* cnt, void* stream);
+
 /* ---- a4: PCG (solver_tol, examples/recons_waymo.py:33; verbose, models/nksr_net.py:97) ---- */
 NKSR_API int nksr_spmv(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
               float* y, int64_t n, void* stream);
@@ -180,6 +191,20 @@ NKSR_API int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const flo
                    const float* diag, const float* b, float* x, int64_t n, float tol,
                    int max_iter, int check_every, int profile, void* ws, size_t ws_bytes,
                    double* info, void* stream);
+
+/* -- the same PCG with the SpMV streamed through the TMA engine (csrc/spmv_stream.cuh): the (col, val) arrays are cut
+ * into tiles of 4096 entries that one elected thread per CTA moves into a shared-memory ring with bulk async copies
+ * (cp.async.bulk + mbarrier); consumer warps form the products in place and reduce the rows from shared memory.  Same
+ * result up to the summation order inside a row (fixed, reproducible).  Bulk copies move whole 16-byte units: rowptr
+ * must be readable up to index n + 1 (n + 2 entries) and col / val up to the next multiple of 4 entries. */
+NKSR_API size_t nksr_pcg_stream_workspace_bytes(int64_t n, int64_t nnz);
+NKSR_API int nksr_pcg_solve_stream(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag,
+                          const float* b, float* x, int64_t n, int64_t nnz, float tol, int max_iter, int check_every,
+                          int profile, void* ws, size_t ws_bytes, double* info, void* stream);
+/* y = A x through the same tile stream (plan_buf: nksr_spmv_plan_bytes(nnz) bytes of scratch) */
+NKSR_API size_t nksr_spmv_plan_bytes(int64_t nnz);
+NKSR_API int nksr_spmv_stream(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
+                     int64_t n, int64_t nnz, void* plan_buf, size_t plan_bytes, void* stream);
 
 /* ---- e: step kernels of the multi-GPU solve (one global system, SURVEY section 8e mapping B).  A
  * Chronopoulos-Gear arrangement of the same Jacobi-PCG: per iteration ONE halo exchange of u = M^-1 r, one
@@ -262,6 +287,17 @@ NKSR_API int nksr_voxel_pca_normals(const int32_t* nbr27, const float* mom10, in
 NKSR_API int nksr_orient_normals(const float* xyz, const float* sensor, const int32_t* base,
                         const float* vox_normal, int64_t m, float cos_min, float* normal,
                         int32_t* keep, void* stream);
+
+/* exact k-nearest-neighbour PCA normals (k <= 64, self included) on a multi-level voxel hash of Morton-SORTED points:
+ * svh = hierarchy of the points' containing voxels (level l: voxel size voxel_size * 2^l), base[l*m + i] = containing
+ * voxel of point i, range = nksr_row_ranges of every level (concatenated in level order).  Per point the finest level
+ * whose 27-voxel block holds >= 3k points is searched; the result is exact when the k-th distance <= that voxel size,
+ * otherwise the search repeats one level coarser (points still inexact on the coarsest level are counted in *inexact,
+ * nullable).  normal: unit eigenvector of the smallest covariance eigenvalue, flipped towards `sensor` (nullable);
+ * keep (nullable) = |cos(view, normal)| > cos_min; eig (nullable): [m][3] ascending eigenvalues. */
+NKSR_API int nksr_knn_normals(const nksr_svh_t* svh, const float* xyz, const float* sensor, const int32_t* base,
+                     const int32_t* range, int64_t m, int k, float cos_min, float* normal, int32_t* keep,
+                     float* eig, int32_t* inexact, void* stream);
 
 #ifdef __cplusplus
 }

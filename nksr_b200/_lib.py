@@ -76,10 +76,16 @@ _SIGNATURES = {
     "nksr_gram_count_own": ("i", "Spp"),
     "nksr_gram_place": ("i", "Siipppp" + "p"),
     "nksr_gram_fill_placed": ("i", "SFKppPppppp"),
+    "nksr_gram_fill_grouped": ("i", "SFKppPppppp"),
+    "nksr_gram_count_grouped": ("i", "Spp"),
     "nksr_nbr125_search": ("i", "pqpp"),
     "nksr_spmv": ("i", "pppppqp"),
     "nksr_pcg_workspace_bytes": ("z", "q"),
     "nksr_pcg_solve": ("i", "pppppp" + "qfiii" + "pzdp"),
+    "nksr_pcg_stream_workspace_bytes": ("z", "qq"),
+    "nksr_pcg_solve_stream": ("i", "pppppp" + "qqfiii" + "pzdp"),
+    "nksr_spmv_plan_bytes": ("z", "q"),
+    "nksr_spmv_stream": ("i", "ppppp" + "qq" + "pzp"),
     "nksr_dcg_workspace_bytes": ("z", ""),
     "nksr_dcg_init": ("i", "pppppppp" + "q" + "pz" + "pp"),
     "nksr_dcg_begin": ("i", "ppfip"),
@@ -106,6 +112,7 @@ _SIGNATURES = {
     "nksr_voxel_moments": ("i", "pqppfpp"),
     "nksr_voxel_pca_normals": ("i", "ppqfpp"),
     "nksr_orient_normals": ("i", "ppppqfppp"),
+    "nksr_knn_normals": ("i", "Spppp" + "qif" + "ppppp"),
 }
 
 _lib = None

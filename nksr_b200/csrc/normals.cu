@@ -121,6 +121,163 @@ __global__ void k_orient_normals(const float* __restrict__ xyz, const float* __r
   keep[i] = (b >= 0 && fabsf(c) > cos_min) ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Exact k-nearest-neighbour PCA normals (examples/recons_waymo_cpu.py:26: pcu.estimate_point_cloud_normals_knn
+// (xyz, 64)), on a multi-level voxel hash of the Morton-sorted points.  One warp per point:
+//   * pick the finest level whose 27-voxel block around the point holds >= 3k points (then the k-th neighbour
+//     lies, for surface-like data, within one voxel size of the point);
+//   * stream the block's points (contiguous ranges: the points are sorted by Morton key), keep the candidates
+//     closer than the current bound in a 128-entry shared-memory buffer, and whenever it fills sort it (bitonic
+//     network on packed (distance, index) words) and keep the k best, tightening the bound;
+//   * the answer is EXACT when the k-th distance does not exceed the voxel size of the level (everything closer
+//     than that lies inside the block); otherwise repeat one level coarser.
+// Then the 3 x 3 covariance of the k neighbours (self included) about their mean, its eigenvector of the smallest
+// eigenvalue (Jacobi, fp64), orientation to the sensor side and the grazing-angle flag.
+constexpr int kKnnWarps = 8;
+constexpr int kKnnBuf = 128;
+
+__device__ __forceinline__ void knn_sort128(unsigned long long* __restrict__ key, int lane) {
+  // ascending bitonic sort of 128 packed words by one warp
+  for (int k = 2; k <= kKnnBuf; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int q0 = 0; q0 < kKnnBuf / 2; q0 += 32) {
+        const int q = q0 + lane;
+        const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+        const int hi = lo | j;
+        const unsigned long long a = key[lo], b = key[hi];
+        if ((a > b) == ((lo & k) == 0)) { key[lo] = b; key[hi] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kKnnWarps * 32)
+k_knn_normals(const nksr_svh_t svh, const float* __restrict__ xyz, const float* __restrict__ sensor,
+              const int32_t* __restrict__ base, const int32_t* __restrict__ range, const int64_t m, const int k,
+              const float cos_min, float* __restrict__ normal, int32_t* __restrict__ keep,
+              float* __restrict__ eig, int32_t* __restrict__ inexact) {
+  __shared__ unsigned long long buf[kKnnWarps][kKnnBuf];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t i = blockIdx.x * (int64_t)kKnnWarps + wid;
+  if (i >= m) return;
+  unsigned long long* key = buf[wid];
+  const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
+  const int L = svh.depth;
+  const unsigned long long kInf = 0xffffffffffffffffull;
+  int got = 0;
+  bool exact = false;
+  for (int l = 0; l < L; ++l) {
+    const int b = __ldg(base + (int64_t)l * m + i);
+    int rb = 0, re = 0;
+    if (b >= 0 && lane < 27) {
+      const int v = __ldg(svh.nbr27[l] + (int64_t)b * 27 + lane);
+      if (v >= 0) {
+        const int2 r = __ldg(reinterpret_cast<const int2*>(range) + svh.offset[l] + v);
+        rb = r.x; re = r.y;
+      }
+    }
+    int total = re - rb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (total < 3 * k && l + 1 < L) continue;
+    // ---- scan the block
+    for (int t = lane; t < kKnnBuf; t += 32) key[t] = kInf;
+    __syncwarp();
+    int fill = 0;                       // entries of the buffer in use (kept best first after a sort)
+    float bound = 3.0e38f;              // candidates at or beyond this squared distance cannot be among the k best
+    for (int s = 0; s < 27; ++s) {
+      const int sb = __shfl_sync(0xffffffffu, rb, s), se = __shfl_sync(0xffffffffu, re, s);
+      for (int q0 = sb; q0 < se; q0 += 32) {
+        const int q = q0 + lane;
+        float d2 = 3.0e38f;
+        if (q < se) {
+          const float dx = __ldg(xyz + 3 * (int64_t)q) - px, dy = __ldg(xyz + 3 * (int64_t)q + 1) - py,
+                      dz = __ldg(xyz + 3 * (int64_t)q + 2) - pz;
+          d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        }
+        const bool in = q < se && d2 < bound;
+        const unsigned bm = __ballot_sync(0xffffffffu, in);
+        if (fill + __popc(bm) > kKnnBuf) {       // no room: keep the k best, tighten the bound
+          knn_sort128(key, lane);
+          for (int t = k + lane; t < kKnnBuf; t += 32) key[t] = kInf;
+          fill = fill < k ? fill : k;
+          if (fill == k) bound = __uint_as_float((unsigned)(key[k - 1] >> 32));
+          __syncwarp();
+        }
+        const bool in2 = in && d2 < bound;
+        const unsigned bm2 = __ballot_sync(0xffffffffu, in2);
+        if (in2) key[fill + __popc(bm2 & ((1u << lane) - 1u))] =
+            ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)q;
+        fill += __popc(bm2);
+        __syncwarp();
+      }
+    }
+    knn_sort128(key, lane);
+    got = fill < k ? fill : k;
+    const float dk2 = got > 0 ? __uint_as_float((unsigned)(key[got - 1] >> 32)) : 0.f;
+    const float hl = svh.voxel_size * (float)(1 << l);
+    exact = got == k && dk2 <= hl * hl;
+    if (exact || l + 1 == L) break;
+  }
+  // ---- covariance of the neighbours about their mean (coordinates relative to the query point)
+  float s[9];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) s[a] = 0.f;
+  for (int t = lane; t < got; t += 32) {
+    const int q = (int)(unsigned)(key[t] & 0xffffffffull);
+    const float dx = __ldg(xyz + 3 * (int64_t)q) - px, dy = __ldg(xyz + 3 * (int64_t)q + 1) - py,
+                dz = __ldg(xyz + 3 * (int64_t)q + 2) - pz;
+    s[0] += dx; s[1] += dy; s[2] += dz;
+    s[3] = fmaf(dx, dx, s[3]); s[4] = fmaf(dx, dy, s[4]); s[5] = fmaf(dx, dz, s[5]);
+    s[6] = fmaf(dy, dy, s[6]); s[7] = fmaf(dy, dz, s[7]); s[8] = fmaf(dz, dz, s[8]);
+  }
+#pragma unroll
+  for (int a = 0; a < 9; ++a) s[a] = warp_sum(s[a]);
+  if (lane != 0) return;
+  float out[3] = {0.f, 0.f, 1.f};
+  double ev[3] = {0.0, 0.0, 0.0};
+  if (got >= 3) {
+    const double ic = 1.0 / (double)got;
+    const double mx = s[0] * ic, my = s[1] * ic, mz = s[2] * ic;
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    a[0][0] = s[3] * ic - mx * mx; a[0][1] = a[1][0] = s[4] * ic - mx * my; a[0][2] = a[2][0] = s[5] * ic - mx * mz;
+    a[1][1] = s[6] * ic - my * my; a[1][2] = a[2][1] = s[7] * ic - my * mz; a[2][2] = s[8] * ic - mz * mz;
+    for (int sweep = 0; sweep < 8; ++sweep) {
+      jacobi_rotate(a, v, 0, 1);
+      jacobi_rotate(a, v, 0, 2);
+      jacobi_rotate(a, v, 1, 2);
+    }
+    int c = 0;
+    if (a[1][1] < a[c][c]) c = 1;
+    if (a[2][2] < a[c][c]) c = 2;
+    const double nx = v[0][c], ny = v[1][c], nz = v[2][c];
+    const double nn = sqrt(nx * nx + ny * ny + nz * nz);
+    if (nn > 0) { out[0] = (float)(nx / nn); out[1] = (float)(ny / nn); out[2] = (float)(nz / nn); }
+    ev[0] = a[0][0]; ev[1] = a[1][1]; ev[2] = a[2][2];
+  }
+  float vx = 0.f, vy = 0.f, vz = 0.f, cs = 1.f;
+  if (sensor) {
+    vx = __ldg(sensor + 3 * i) - px; vy = __ldg(sensor + 3 * i + 1) - py; vz = __ldg(sensor + 3 * i + 2) - pz;
+    const float vn = sqrtf(vx * vx + vy * vy + vz * vz) + 1e-6f;   // examples/recons_waymo_cpu.py:32-33
+    vx /= vn; vy /= vn; vz /= vn;
+    cs = vx * out[0] + vy * out[1] + vz * out[2];
+    if (cs < 0.f) { out[0] = -out[0]; out[1] = -out[1]; out[2] = -out[2]; }   // :34-36
+  }
+  normal[3 * i] = out[0]; normal[3 * i + 1] = out[1]; normal[3 * i + 2] = out[2];
+  if (keep) keep[i] = (got >= 3 && fabsf(cs) > cos_min) ? 1 : 0;               // :38-39
+  if (eig) {   // ascending eigenvalues (tests skip degenerate neighbourhoods)
+    double e0 = ev[0], e1 = ev[1], e2 = ev[2], tsw;
+    if (e0 > e1) { tsw = e0; e0 = e1; e1 = tsw; }
+    if (e1 > e2) { tsw = e1; e1 = e2; e2 = tsw; }
+    if (e0 > e1) { tsw = e0; e0 = e1; e1 = tsw; }
+    eig[3 * i] = (float)e0; eig[3 * i + 1] = (float)e1; eig[3 * i + 2] = (float)e2;
+  }
+  if (inexact && !exact) atomicAdd(inexact, 1);
+}
+
 }  // namespace
 
 extern "C" {
@@ -146,6 +303,18 @@ int nksr_orient_normals(const float* xyz, const float* sensor, const int32_t* ba
   if (m == 0) return NKSR_OK;
   k_orient_normals<<<grid_for(m, 256), 256, 0, as_stream(stream)>>>(xyz, sensor, base, vox_normal, m, cos_min,
                                                                      normal, keep);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_knn_normals(const nksr_svh_t* svh, const float* xyz, const float* sensor, const int32_t* base,
+                     const int32_t* range, int64_t m, int k, float cos_min, float* normal, int32_t* keep, float* eig,
+                     int32_t* inexact, void* stream) {
+  if (!svh || !xyz || !base || !range || !normal || k < 3 || k > 64 || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH)
+    return NKSR_E_INVALID;
+  if (m == 0) return NKSR_OK;
+  k_knn_normals<<<grid_for(m, kKnnWarps), kKnnWarps * 32, 0, as_stream(stream)>>>(*svh, xyz, sensor, base, range, m, k,
+                                                                                cos_min, normal, keep, eig, inexact);
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

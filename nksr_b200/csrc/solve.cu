@@ -17,6 +17,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "spmv_stream.cuh"
 
 namespace {
 
@@ -235,11 +236,17 @@ static PcgWs carve(void* ws, int64_t n) {
 
 // one PCG iteration on stream s (rz buffers alternate with the iteration parity)
 static void launch_iteration(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag, float* x,
-                             int64_t n, const PcgWs& w, int parity, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
+                             int64_t n, const PcgWs& w, int parity, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1,
+                             const SpmvPlan* plan) {
   double* rz_cur = parity ? w.rz1 : w.rz0;
   double* rz_new = parity ? w.rz0 : w.rz1;
   if (e0) cudaEventRecord(e0, s);
-  k_spmv<true><<<kGrid, kBlock, 0, s>>>(rowptr, col, val, w.p, w.ap, n, w.pap, w.ctrl);
+  if (plan) {   // tile stream through the TMA engine + boundary rows + p.Ap
+    spmv_stream_launch(rowptr, col, val, w.p, w.ap, n, *plan, &w.ctrl->done, s);
+    k_dot_partials<<<kGrid, 256, 0, s>>>(w.p, w.ap, n, w.pap, &w.ctrl->done);
+  } else {
+    k_spmv<true><<<kGrid, kBlock, 0, s>>>(rowptr, col, val, w.p, w.ap, n, w.pap, w.ctrl);
+  }
   if (e1) cudaEventRecord(e1, s);
   k_pcg_update<<<kGrid, kBlock, 0, s>>>(diag, w.p, w.ap, x, w.r, n, rz_cur, w.pap, rz_new, w.rr, w.ctrl);
   k_pcg_direction<<<kGrid, kBlock, 0, s>>>(w.ap, w.p, n, rz_cur, rz_new, w.rr, w.ctrl);
@@ -271,9 +278,11 @@ size_t nksr_pcg_workspace_bytes(int64_t n) {
          align256(sizeof(PcgCtrl)) + 256;
 }
 
-int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag, const float* b,
-                   float* x, int64_t n, float tol, int max_iter, int check_every, int profile, void* ws,
-                   size_t ws_bytes, double* info, void* stream) {
+}  // extern "C"
+
+static int pcg_solve_impl(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag,
+                          const float* b, float* x, int64_t n, float tol, int max_iter, int check_every, int profile,
+                          void* ws, size_t ws_bytes, double* info, void* stream, const SpmvPlan* plan) {
   if (n <= 0 || !info || max_iter < 0) return NKSR_E_INVALID;
   if (ws_bytes < nksr_pcg_workspace_bytes(n)) return NKSR_E_WORKSPACE;
   if (check_every < 1) check_every = 1;
@@ -301,7 +310,7 @@ int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val, 
       for (int j = 0; j < check_every && launched < max_iter; ++j, ++launched) {
         const bool timed = n_ev < kMaxEv;
         launch_iteration(rowptr, col, val, diag, x, n, w, launched & 1, s, timed ? ev[2 * n_ev] : nullptr,
-                         timed ? ev[2 * n_ev + 1] : nullptr);
+                         timed ? ev[2 * n_ev + 1] : nullptr, plan);
         if (timed) ++n_ev;
       }
       rc = read_ctrl(w.ctrl, &host, s);
@@ -332,7 +341,7 @@ int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val, 
       ok = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
       if (ok) {
         for (int j = 0; j < per_graph; ++j)
-          launch_iteration(rowptr, col, val, diag, x, n, w, j & 1, cap, nullptr, nullptr);
+          launch_iteration(rowptr, col, val, diag, x, n, w, j & 1, cap, nullptr, nullptr, plan);
         ok = cudaStreamEndCapture(cap, &graph) == cudaSuccess && graph != nullptr;
       }
       if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
@@ -357,6 +366,46 @@ int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val, 
   info[1] = host.bb > 0.0 ? sqrt(host.rr / host.bb) : 0.0;
   info[4] = (double)(host.done == 1 ? 0 : (host.done == 2 ? 2 : 1));   // 0 converged, 1 max_iter, 2 NaN
   return NKSR_OK;
+}
+
+extern "C" {
+
+int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag, const float* b,
+                   float* x, int64_t n, float tol, int max_iter, int check_every, int profile, void* ws,
+                   size_t ws_bytes, double* info, void* stream) {
+  return pcg_solve_impl(rowptr, col, val, diag, b, x, n, tol, max_iter, check_every, profile, ws, ws_bytes, info,
+                        stream, nullptr);
+}
+
+size_t nksr_pcg_stream_workspace_bytes(int64_t n, int64_t nnz) {
+  return nksr_pcg_workspace_bytes(n) + spmv_plan_bytes(nnz > 0 ? nnz : 1);
+}
+
+int nksr_pcg_solve_stream(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag,
+                          const float* b, float* x, int64_t n, int64_t nnz, float tol, int max_iter, int check_every,
+                          int profile, void* ws, size_t ws_bytes, double* info, void* stream) {
+  if (n <= 0 || nnz <= 0) return NKSR_E_INVALID;
+  if (ws_bytes < nksr_pcg_stream_workspace_bytes(n, nnz)) return NKSR_E_WORKSPACE;
+  const size_t base = nksr_pcg_workspace_bytes(n);
+  SpmvPlan plan = spmv_plan_carve(reinterpret_cast<unsigned char*>(ws) + base, nnz);
+  if (spmv_stream_prepare() != NKSR_OK || spmv_stream_sm_count() <= 0) return NKSR_E_CUDA;
+  if (spmv_plan_build(rowptr, n, plan, as_stream(stream)) != NKSR_OK) return NKSR_E_CUDA;
+  return pcg_solve_impl(rowptr, col, val, diag, b, x, n, tol, max_iter, check_every, profile, ws, base, info, stream,
+                        &plan);
+}
+
+size_t nksr_spmv_plan_bytes(int64_t nnz) { return spmv_plan_bytes(nnz > 0 ? nnz : 1); }
+
+int nksr_spmv_stream(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, float* y, int64_t n,
+                     int64_t nnz, void* plan_buf, size_t plan_bytes, void* stream) {
+  if (n <= 0 || nnz <= 0 || !plan_buf) return NKSR_E_INVALID;
+  if (plan_bytes < spmv_plan_bytes(nnz)) return NKSR_E_WORKSPACE;
+  cudaStream_t s = as_stream(stream);
+  SpmvPlan plan = spmv_plan_carve(plan_buf, nnz);
+  if (spmv_stream_prepare() != NKSR_OK) return NKSR_E_CUDA;
+  if (spmv_plan_build(rowptr, n, plan, s) != NKSR_OK) return NKSR_E_CUDA;
+  if (cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), s) != cudaSuccess) return NKSR_E_CUDA;   // empty rows
+  return spmv_stream_launch(rowptr, col, val, x, y, n, plan, nullptr, s);
 }
 
 }  // extern "C"

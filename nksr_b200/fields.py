@@ -173,13 +173,25 @@ class KernelField(BaseField):
         dev, n = self.svh.device, sysm.n
         tm = getattr(self, "_timer", None) or _lib.StageTimer(dev, enabled=False)
         alpha = torch.empty(n, dtype=torch.float32, device=dev)
-        nb = call("nksr_pcg_workspace_bytes", n)
-        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         info = (C.c_double * 8)()
         profile = int(bool(self.solver_config.get("profile")))
-        call("nksr_pcg_solve", sysm.rowptr, sysm.col, sysm.val, sysm.diag, sysm.rhs, alpha, n,
-             float(self.solver_config["tol"]), int(self.solver_config["max_iter"]),
-             int(self.solver_config["check_every"]), profile, ws, nb, info, stream_ptr(dev))
+        # 'stream' (default): the CSR arrays reach the SMs as tiles moved by bulk async copies (TMA engine) into a
+        # shared-memory ring (csrc/spmv_stream.cuh); 'rows': one warp per row with register loads (csrc/solve.cu)
+        spmv = self.solver_config.get("spmv") or os.environ.get("NKSR_SPMV") or "stream"
+        if spmv not in ("stream", "rows"):
+            raise ValueError("solver_config['spmv'] must be 'stream' or 'rows'")
+        if spmv == "stream":
+            nb = call("nksr_pcg_stream_workspace_bytes", n, sysm.nnz)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            call("nksr_pcg_solve_stream", sysm.rowptr, sysm.col, sysm.val, sysm.diag, sysm.rhs, alpha, n, sysm.nnz,
+                 float(self.solver_config["tol"]), int(self.solver_config["max_iter"]),
+                 int(self.solver_config["check_every"]), profile, ws, nb, info, stream_ptr(dev))
+        else:
+            nb = call("nksr_pcg_workspace_bytes", n)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            call("nksr_pcg_solve", sysm.rowptr, sysm.col, sysm.val, sysm.diag, sysm.rhs, alpha, n,
+                 float(self.solver_config["tol"]), int(self.solver_config["max_iter"]),
+                 int(self.solver_config["check_every"]), profile, ws, nb, info, stream_ptr(dev))
         tm.mark("pcg")
         self.alpha = alpha
         status = int(info[4])                       # 0 converged, 1 max_iter reached, 2 NaN / breakdown
@@ -246,7 +258,9 @@ class KernelField(BaseField):
             # transposed entries go straight to their final slot (SPEC S6b): per (fine level, offset) pair
             # a rank table on the fine level and a 125-ancestor prefix table on the coarse level
             cnt_down = torch.zeros(n, dtype=torch.int32, device=dev)
-            call("nksr_gram_count_own", svh.view(), cnt, st)
+            grouped = (self.solver_config.get("fill") or os.environ.get("NKSR_FILL") or "grouped") == "grouped" \
+                and svh.depth <= 4 and svh.depth < _lib.MAX_DEPTH
+            call("nksr_gram_count_grouped" if grouped else "nksr_gram_count_own", svh.view(), cnt, st)
             place = _lib.PlacementT()
             for l in range(svh.depth - 1):
                 for k in range(1, svh.depth - l):
@@ -262,7 +276,8 @@ class KernelField(BaseField):
         else:
             cnt_down = torch.empty(n, dtype=torch.int32, device=dev)
             call("nksr_gram_count", svh.view(), cnt, cnt_down, st)
-        rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        # (one spare row pointer, and below 4 spare entries of col / val: the streamed SpMV moves 16-byte units)
+        rowptr = torch.zeros(n + 2, dtype=torch.int64, device=dev)[:n + 1]
         nb = call("nksr_scan_workspace_bytes", n)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         call("nksr_gram_rowptr", cnt, cnt_down, n, rowptr, ws, nb, st)
@@ -296,11 +311,19 @@ class KernelField(BaseField):
                 cs.mblocks = mblocks.data_ptr()
                 keep.append(mblocks)
                 tm.mark("gram_blocks")
-        col = torch.empty(nnz, dtype=torch.int32, device=dev)
-        val = torch.empty(nnz, dtype=torch.float32, device=dev)
+        col = torch.empty(nnz + 4, dtype=torch.int32, device=dev)[:nnz]
+        val = torch.empty(nnz + 4, dtype=torch.float32, device=dev)[:nnz]
         rhs = torch.empty(n, dtype=torch.float32, device=dev)
         diag = torch.zeros(n, dtype=torch.float32, device=dev)
-        if place is not None:
+        # numeric phase.  'grouped' (default): one warp per sibling group -- eight rows share their constraint
+        # lines, column tables and flush indices (csrc/gram_fill_group.cu); 'rows': one warp per matrix row
+        # (csrc/assemble.cu), kept for hierarchies deeper than 4 levels and as the comparison variant
+        fill = self.solver_config.get("fill") or os.environ.get("NKSR_FILL") or "grouped"
+        if fill not in ("grouped", "rows"):
+            raise ValueError("solver_config['fill'] must be 'grouped' or 'rows'")
+        if place is not None and fill == "grouped" and svh.depth <= 4 and svh.depth < _lib.MAX_DEPTH:
+            call("nksr_gram_fill_grouped", svh.view(), self.feat_view(), cs, cnt, rowptr, place, col, val, rhs, diag, st)
+        elif place is not None:
             call("nksr_gram_fill_placed", svh.view(), self.feat_view(), cs, cnt, rowptr, place, col, val, rhs, diag, st)
         else:
             cursor = torch.zeros(n, dtype=torch.int32, device=dev)

@@ -14,6 +14,7 @@ open training model, models/nksr_net.py:57-133, including its constraint weights
 from __future__ import annotations
 
 import math
+from types import SimpleNamespace
 from typing import Callable, List, Optional
 
 import torch
@@ -56,11 +57,79 @@ def voxel_size_from_detail(xyz: torch.Tensor, detail_level: float) -> float:
     return math.sqrt(lo * hi)
 
 
-def get_estimate_normal_preprocess_fn(knn: int = 64, max_angle_deg: float = 85.0) -> Callable:
-    """Normal estimation + sensor-side orientation + grazing-angle filter, following the open CPU
-    twin examples/recons_waymo_cpu.py:21-41.  Neighbourhoods are voxel neighbourhoods sized to
-    hold ~knn points (PCA over the 27 voxels around the point) instead of exact kNN -- SURVEY
-    section 8(f) row 1 ('next'); runs in PyTorch on the device."""
+KNN_LEVELS = 7        # levels of the voxel hash behind the kNN search (cell size doubles per level)
+
+
+def _knn_hash(xyz: torch.Tensor, levels: int = KNN_LEVELS):
+    """Multi-level voxel hash of a cloud for neighbour searches: returns (perm, svh, base, ranges) with the points
+    Morton-sorted by `perm`, the hierarchy of their containing voxels (finest cell ~ a sixth of the mean point
+    spacing, doubling per level), base[l][i] = containing voxel of sorted point i, ranges[offset_l + v] = [first,
+    last) sorted point of voxel v.  Keys are taken on coordinates shifted to the bounding-box corner."""
+    dev, st = xyz.device, stream_ptr(xyz.device)
+    n = xyz.shape[0]
+    lo = xyz.min(dim=0).values
+    ext = (xyz.max(dim=0).values - lo).tolist()                      # the one host read of the set-up
+    emax = max(max(ext), 1e-12)
+    dims = [max(e, 1e-3 * emax) for e in ext]
+    h0 = 0.15 * (dims[0] * dims[1] * dims[2] / max(n, 1)) ** (1.0 / 3.0)
+    h0 = float(torch.tensor(max(h0, emax / 2.0 ** 17), dtype=torch.float32).item())
+    shifted = (xyz - lo).contiguous()
+    hk = torch.empty(n, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("nksr_point_half_keys", shifted, n, h0, hk, status, st)
+    hk_sorted, perm = _lib.sort_pairs(hk, torch.arange(n, dtype=torch.int32, device=dev))
+    perm = perm.long()
+    shifted = shifted[perm].contiguous()
+    keys = [_lib.unique_sorted(hk_sorted, 3 * (l + 1)) for l in range(levels)]
+    svh = SparseFeatureHierarchy(h0, levels, dev).build_from_keys(keys)
+    base = svh.locate(shifted)
+    offs = svh.offsets
+    ranges = torch.empty((svh.num_unknowns, 2), dtype=torch.int32, device=dev)
+    for l in range(levels):
+        call("nksr_row_ranges", base[l], n, ranges[offs[l]:], svh.num_voxels(l), st)
+    return perm, svh, base, ranges
+
+
+def estimate_normals_knn(xyz: torch.Tensor, sensor: Optional[torch.Tensor], knn: int = 64,
+                         max_angle_deg: float = 85.0, want_eig: bool = False):
+    """Exact kNN-PCA normals (csrc/normals.cu: k_knn_normals).  Returns the Morton permutation, the normals (in
+    permuted order, flipped towards `sensor` when given), the keep flags of the grazing-angle filter, optionally
+    the covariance eigenvalues, and the number of points whose neighbourhood could not be proven exact."""
+    _lib.require_cuda(xyz, "xyz")
+    xyz = xyz.detach().to(torch.float32).contiguous()
+    n = xyz.shape[0]
+    k = min(int(knn), 64, n)
+    if k < 3:
+        raise _lib.NksrError("normal estimation needs at least 3 points")
+    dev, st = xyz.device, stream_ptr(xyz.device)
+    perm, svh, base, ranges = _knn_hash(xyz)
+    xs = xyz[perm].contiguous()
+    ss = sensor.detach().to(torch.float32)[perm].contiguous() if sensor is not None else None
+    nrm = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    keep = torch.empty(n, dtype=torch.int32, device=dev)
+    eig = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_eig else None
+    inexact = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("nksr_knn_normals", svh.view(), xs, ss, base, ranges, n, k, math.cos(math.radians(max_angle_deg)), nrm, keep,
+         eig, inexact, st)
+    return SimpleNamespace(perm=perm, xyz=xs, sensor=ss, normal=nrm, keep=keep, eig=eig, inexact=inexact)
+
+
+def get_estimate_normal_preprocess_fn(knn: int = 64, max_angle_deg: float = 85.0, mode: str = "knn") -> Callable:
+    """Normal estimation + sensor-side orientation + grazing-angle filter, following the open CPU twin
+    examples/recons_waymo_cpu.py:21-41 line by line: k-nearest-neighbour PCA normals (:26), unit view direction
+    (:32-33), flip (:34-36), |cos| > cos(max_angle) filter (:38-39).  mode='knn' (default): exact kNN on a
+    multi-level voxel hash, one warp per point; mode='voxel': the round-1 approximation (PCA over the 27 voxels
+    around the point of a grid sized to hold ~knn points; every point of a voxel gets the same normal)."""
+    if mode not in ("knn", "voxel"):
+        raise ValueError("mode must be 'knn' or 'voxel'")
+
+    def fn_knn(xyz: torch.Tensor, normal: Optional[torch.Tensor], sensor: Optional[torch.Tensor]):
+        assert normal is None, "normal already exists"
+        assert sensor is not None, "please provide sensor positions for consistent orientations"
+        r = estimate_normals_knn(xyz, sensor, knn, max_angle_deg)
+        scan = _lib.exclusive_scan32(r.keep)
+        cnt = int(scan[-1].item())
+        return _lib.compact_rows(r.xyz, r.keep, scan, cnt), _lib.compact_rows(r.normal, r.keep, scan, cnt), None
 
     def fn(xyz: torch.Tensor, normal: Optional[torch.Tensor], sensor: Optional[torch.Tensor]):
         assert normal is None, "normal already exists"
@@ -105,7 +174,7 @@ def get_estimate_normal_preprocess_fn(knn: int = 64, max_angle_deg: float = 85.0
         cnt = int(scan[-1].item())
         return _lib.compact_rows(xs, keep, scan, cnt), _lib.compact_rows(nrm, keep, scan, cnt), None
 
-    return fn
+    return fn_knn if mode == "knn" else fn
 
 
 class ChunkedField(BaseField):

@@ -1,0 +1,134 @@
+"""nksr.get_estimate_normal_preprocess_fn(knn=64, max_angle_deg=85) -- the CUDA kNN-PCA kernel
+(csrc/normals.cu: k_knn_normals, multi-level voxel hash, one warp per point) against the CPU restatement of the
+reference's open twin examples/recons_waymo_cpu.py:21-41 (oracle/normals.py: scipy cKDTree kNN + numpy eigh).
+
+  * the neighbourhoods are EXACT: no point is reported inexact, and the normals agree with the oracle's up to sign
+    within 1e-3 wherever the covariance has a clear smallest eigenvalue (a near-degenerate neighbourhood has no
+    well-defined normal: both sides may return any vector of the eigenspace)
+  * flip towards the sensor and the |cos| > cos(85 deg) filter: identical keep mask away from the threshold
+  * edge cases: fewer points than k, duplicates, a cloud far from the origin, a planar cloud
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import normals as ON
+from tests import clouds, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _run(cuda, xyz, sensor, k=64):
+    from nksr_b200.reconstructor import estimate_normals_knn
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    r = estimate_normals_knn(t(xyz), t(sensor) if sensor is not None else None, k, 85.0, want_eig=True)
+    perm = _np(r.perm)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    return _np(r.normal)[inv], _np(r.keep)[inv].astype(bool), _np(r.eig)[inv], int(r.inexact.item())
+
+
+def _compare(xyz, sensor, n_gpu, keep_gpu, eig_gpu, k=64, min_frac=0.999):
+    kk = min(k, xyz.shape[0])
+    idx, _ = ON.knn_indices(xyz, kk)
+    n_ref, ev = ON.pca_normals(xyz, idx)
+    # eigenvalues agree (covariance of the same neighbour set)
+    scale = ev[:, 2].max()
+    assert np.abs(np.sort(eig_gpu, axis=1) - ev).max() <= 2e-4 * scale
+    clear = (ev[:, 1] - ev[:, 0]) > 0.05 * ev[:, 2]          # a well-defined smallest eigen-direction
+    assert clear.mean() > 0.5
+    dots = np.abs(np.sum(n_gpu.astype(np.float64) * n_ref, axis=1))
+    ok = dots[clear] >= 1.0 - 5e-7                            # angle <= 1e-3 rad
+    assert ok.mean() >= min_frac, f"only {ok.mean():.5f} of the well-defined normals agree"
+    if sensor is not None:
+        view = sensor.astype(np.float64) - xyz.astype(np.float64)
+        view /= (np.linalg.norm(view, axis=1, keepdims=True) + 1e-6)
+        cos_ref = np.sum(view * n_ref, axis=1)
+        thr = np.cos(np.deg2rad(85.0))
+        away = clear & (np.abs(np.abs(cos_ref) - thr) > 2e-3)
+        assert np.array_equal(keep_gpu[away], (np.abs(cos_ref) > thr)[away])
+        # orientation: towards the sensor
+        cos_gpu = np.sum(view * n_gpu, axis=1)
+        assert (cos_gpu[clear] >= -1e-6).all()
+
+
+@pytest.mark.parametrize("scene,n", [("cfg4_outdoor", 120_000), ("cfg3_indoor", 80_000)])
+def test_knn_normals_match_oracle_on_bench_scenes(cuda, scene, n):
+    xyz, sensor, _ = scenes.crop(scene, n, with_sensor=True)
+    n_gpu, keep, eig, inexact = _run(cuda, xyz, sensor)
+    assert inexact == 0
+    _compare(xyz, sensor, n_gpu, keep, eig)
+
+
+def test_knn_normals_on_analytic_shapes(cuda):
+    xyz, nrm = clouds.sphere(20_000, noise=0.0005)
+    sensor = np.zeros_like(xyz) + np.array([0.0, 0.0, 5.0], np.float32)
+    n_gpu, keep, eig, inexact = _run(cuda, xyz, sensor)
+    assert inexact == 0
+    _compare(xyz, sensor, n_gpu, keep, eig)
+    # and they are the sphere's normals
+    assert np.abs(np.sum(n_gpu * nrm, axis=1)).mean() > 0.999
+
+
+@pytest.mark.parametrize("case", ["few_points", "duplicates", "far_from_origin", "planar", "k16"])
+def test_knn_normals_edge_cases(cuda, case):
+    rng = np.random.default_rng(2)
+    k = 64
+    if case == "few_points":
+        xyz = rng.normal(size=(40, 3)).astype(np.float32)             # fewer points than k: all of them
+    elif case == "duplicates":
+        base = rng.uniform(-1, 1, size=(3000, 3)).astype(np.float32)
+        base[:, 2] *= 0.02
+        xyz = np.concatenate([base, base[:500]])                      # exact duplicates
+    elif case == "far_from_origin":
+        xyz, _ = clouds.sphere(8000, noise=0.001)
+        xyz = (xyz + np.array([5000.0, -3000.0, 800.0])).astype(np.float32)
+    elif case == "planar":
+        xyz = np.zeros((6000, 3), np.float32)
+        xyz[:, :2] = rng.uniform(-1, 1, size=(6000, 2))
+    else:
+        xyz, _ = clouds.sphere(5000, noise=0.001)
+        k = 16
+    sensor = np.zeros_like(xyz) + np.array([0.3, 0.2, 50.0], np.float32)
+    n_gpu, keep, eig, inexact = _run(cuda, xyz, sensor, k)
+    assert np.isfinite(n_gpu).all() and np.allclose(np.linalg.norm(n_gpu, axis=1), 1.0, atol=1e-5)
+    if case == "planar":
+        assert (np.abs(n_gpu[:, 2]) > 1 - 1e-6).all()
+        return
+    if case == "duplicates":                                          # ties at the k-th distance: set may differ
+        _compare(xyz, sensor, n_gpu, keep, eig, k, min_frac=0.98)
+        return
+    if case == "far_from_origin":                                     # fp32 coordinates: ~1e-3 relative spacing
+        idx, _ = ON.knn_indices(xyz, k)
+        n_ref, ev = ON.pca_normals(xyz, idx)
+        clear = (ev[:, 1] - ev[:, 0]) > 0.05 * ev[:, 2]
+        dots = np.abs(np.sum(n_gpu.astype(np.float64) * n_ref, axis=1))
+        assert (dots[clear] > 1 - 1e-4).mean() > 0.99
+        return
+    _compare(xyz, sensor, n_gpu, keep, eig, k)
+
+
+def test_preprocess_fn_contract(cuda):
+    """fn(xyz, normal=None, sensor) -> (xyz', normal', None) with only the kept points (examples/recons_waymo_cpu.py:
+    21-41), same kept SET as the oracle away from the threshold."""
+    import nksr_b200
+    xyz, sensor, _ = scenes.crop("cfg4_outdoor", 60_000, with_sensor=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    fn = nksr_b200.get_estimate_normal_preprocess_fn(64, 85.0)
+    x2, n2, s2 = fn(t(xyz), None, t(sensor))
+    assert s2 is None and x2.shape == n2.shape and x2.shape[0] <= xyz.shape[0]
+    px, pn, keep, _ = ON.estimate_normal_preprocess(xyz, sensor, 64, 85.0)
+    assert abs(x2.shape[0] - px.shape[0]) <= 0.002 * xyz.shape[0]
+    # every kept GPU point is an input point; compare normals through a lookup by coordinates
+    lut = {tuple(p): nn for p, nn in zip(px.round(6).tolist(), pn)}
+    hit = 0
+    x2n, n2n = _np(x2), _np(n2)
+    for p, nn in zip(x2n[:4000].round(6).tolist(), n2n[:4000]):
+        r = lut.get(tuple(p))
+        if r is not None and abs(float(np.dot(r, nn))) > 1 - 1e-5:
+            hit += 1
+    assert hit >= 0.97 * 4000

@@ -156,7 +156,7 @@ def test_structural_placement_is_the_same_matrix(cuda, L, W, prune):
     out = {}
     for placement in ("sorted", "structural", "structural"):
         field = _field(cuda, svh, feats, False)
-        field.solver_config.update(keep_system=True, max_iter=0, placement=placement)
+        field.solver_config.update(keep_system=True, max_iter=0, placement=placement, fill="rows")
         field.solve(t(xyz), t(nxyz), t(nval), pw, nw, 1.0)
         s = field.system
         out.setdefault(placement, []).append((_np(s.rowptr).copy(), _np(s.col).copy(), _np(s.val).copy(), _gpu_csr(field)))
@@ -168,6 +168,57 @@ def test_structural_placement_is_the_same_matrix(cuda, L, W, prune):
     P = O.structural_pattern(osvh)
     Ab = A_a.copy(); Ab.data[:] = 1
     assert Ab.nnz == P.nnz and (Ab - P).count_nonzero() == 0
+
+
+@pytest.mark.parametrize("L,W,prune,approx,compact,split,normals", [
+    (4, 0.02, False, False, False, None, True),     # bench settings: automatic block split level
+    (4, 0.02, True, True, False, 4, True),          # pruned finest level, no blocks at all
+    (4, 0.02, False, True, True, None, True),       # compact gradient rows (approx_kernel_grad)
+    (4, 0.02, False, False, False, 1, True),        # blocks from level 1 upwards
+    (3, 0.03, False, True, False, 0, True),         # every level through blocks
+    (2, 0.04, False, False, False, None, True),
+    (1, 0.05, False, False, False, None, True),     # single level: rows of the top level only
+    (4, 0.02, False, False, False, None, False),    # position constraints only
+])
+def test_grouped_fill_is_the_row_fill(cuda, L, W, prune, approx, compact, split, normals):
+    """The sibling-group fill (csrc/gram_fill_group.cu, the default) stores the matrix of the row-per-warp fill:
+    identical row pointers and columns (same structural order, same placement of the transposed entries), values /
+    rhs / diagonal equal up to fp32 summation order, and it is run-to-run bitwise reproducible."""
+    import nksr_b200
+    xyz, _ = clouds.shapenet_like(3000)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    osvh = O.OracleSVH(W, L).build_point_splatting(xyz)
+    keys = list(osvh.keys)
+    if prune:
+        keys[0] = keys[0][O.key_to_ijk(keys[0], 0)[:, 0] >= 0]
+        osvh = O.OracleSVH(W, L).build_from_keys(keys)
+    svh = nksr_b200.SparseFeatureHierarchy(W, L, cuda).build_from_keys([t(k) for k in keys])
+    feats = _feats(osvh, 4, 5)
+    nxyz = np.concatenate([osvh.centers(d) for d in range(min(2, L))])
+    rng = np.random.default_rng(3)
+    nxyz = (nxyz + rng.uniform(-0.3, 0.3, nxyz.shape) * W).astype(np.float32)     # off-centre: generic tau
+    nval = -(nxyz / np.linalg.norm(nxyz, axis=1, keepdims=True)).astype(np.float32)
+    pw, nw = 1e4 / xyz.shape[0], 1e4 / nxyz.shape[0] * W * W
+    out = []
+    for fill in ("rows", "grouped", "grouped"):
+        field = _field(cuda, svh, feats, approx)
+        field.solver_config.update(keep_system=True, max_iter=0, fill=fill, compact_rows=compact)
+        if split is not None:
+            field.solver_config["block_split_level"] = split
+        if normals:
+            field.solve(t(xyz), t(nxyz), t(nval), pw, nw, 1.0)
+        else:
+            field.solve(t(xyz), None, None, pw, 0.0, 1.0)
+        s = field.system
+        out.append([_np(a).copy() for a in (s.rowptr, s.col, s.val, s.rhs, s.diag)])
+    (rp_r, col_r, val_r, rhs_r, dg_r), (rp_g, col_g, val_g, rhs_g, dg_g), second = out
+    assert np.array_equal(rp_r, rp_g) and np.array_equal(col_r, col_g)
+    scale = np.abs(val_r).max()
+    assert np.abs(val_r - val_g).max() <= 2e-6 * scale
+    assert np.abs(rhs_r - rhs_g).max() <= 2e-6 * max(np.abs(rhs_r).max(), 1e-30)
+    assert np.abs(dg_r - dg_g).max() <= 2e-6 * scale
+    for a, b in zip(out[1], second):
+        assert np.array_equal(a, b)
 
 
 def test_gram_position_only_and_determinism(cuda):
@@ -208,6 +259,80 @@ def test_spmv_and_pcg_match_oracle(cuda):
     assert np.abs(fo - fg).max() <= 2e-3 * max(np.abs(fo).max(), 1e-3) + 2e-4
     assert abs(field.solve_info["iterations"] - O.pcg(A_ref, b_ref, 1e-6, 5000, dtype=np.float32)[1]) <= \
         0.25 * field.solve_info["iterations"] + 5
+
+
+def _random_csr(n, lengths, seed, cuda):
+    """CSR with the given row lengths (columns random with repeats allowed: SpMV does not care), fp32 values"""
+    rng = np.random.default_rng(seed)
+    rowptr = np.zeros(n + 2, np.int64)
+    rowptr[1:n + 1] = np.cumsum(lengths)
+    nnz = int(rowptr[n])
+    col = rng.integers(0, n, nnz + 4).astype(np.int32)
+    val = rng.normal(size=nnz + 4).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    return t(rowptr)[:n + 1], t(col)[:nnz], t(val)[:nnz], nnz
+
+
+@pytest.mark.parametrize("kind", ["assembled", "ragged", "long_rows", "tiny_rows", "one_tile"])
+def test_streamed_spmv_matches_row_spmv(cuda, kind):
+    """The TMA-streamed SpMV (bulk async copies of 4096-entry tiles, csrc/spmv_stream.cuh) against the warp-per-row
+    kernel and a float64 product: rows cut by tile boundaries (heads added in tile order), rows longer than several
+    tiles, tiles holding more rows than the staged row-pointer slice, a matrix smaller than one tile; and the
+    result is bitwise reproducible."""
+    import nksr_b200._lib as L
+    rng = np.random.default_rng(11)
+    if kind == "assembled":
+        field, *_rest = _solve_setup(cuda)
+        xyz, nxyz, nval, (pw, nw, rw) = _rest[3], _rest[4], _rest[5], _rest[6]
+        field.solver_config.update(keep_system=True, max_iter=0)
+        t = lambda a: torch.from_numpy(a).to(cuda)
+        field.solve(t(xyz), t(nxyz), t(nval), pw, nw, rw)
+        s = field.system
+        rowptr, col, val, nnz = s.rowptr, s.col, s.val, s.nnz
+        n = rowptr.numel() - 1
+    else:
+        n = {"ragged": 30_000, "long_rows": 4_000, "tiny_rows": 200_000, "one_tile": 37}[kind]
+        if kind == "ragged":
+            lengths = rng.choice([1, 7, 120, 213, 317, 900, 5000], n, p=[.05, .1, .3, .3, .2, .04, .01])
+        elif kind == "long_rows":
+            lengths = rng.choice([3, 200, 4096, 9000, 40_000], n, p=[.3, .5, .1, .07, .03])
+        elif kind == "tiny_rows":
+            lengths = rng.choice([1, 2, 3], n)                  # > 512 rows per tile: row pointers read from HBM
+        else:
+            lengths = rng.integers(1, 60, n)
+        rowptr, col, val, nnz = _random_csr(n, lengths, 5, cuda)
+    x = torch.randn(n, device=cuda)
+    y_rows = torch.empty_like(x)
+    L.call("nksr_spmv", rowptr, col, val, x, y_rows, n, L.stream_ptr(cuda))
+    nb = L.call("nksr_spmv_plan_bytes", nnz)
+    plan = torch.empty(nb, dtype=torch.uint8, device=cuda)
+    ys = []
+    for _ in range(2):
+        y = torch.full_like(x, float("nan"))
+        L.call("nksr_spmv_stream", rowptr, col, val, x, y, n, nnz, plan, nb, L.stream_ptr(cuda))
+        ys.append(_np(y).copy())
+    assert np.array_equal(ys[0], ys[1])
+    A = sp.csr_matrix((_np(val).astype(np.float64), _np(col), _np(rowptr)), shape=(n, n))
+    ref = A @ _np(x).astype(np.float64)
+    absA = abs(A) @ np.abs(_np(x)).astype(np.float64)           # scale of the terms of each row sum
+    assert np.all(np.abs(ys[0] - ref) <= 2e-6 * absA + 1e-30)
+    assert np.all(np.abs(_np(y_rows) - ref) <= 2e-6 * absA + 1e-30)
+
+
+def test_streamed_pcg_is_the_row_pcg(cuda):
+    """Same system, PCG with the streamed SpMV against PCG with the row SpMV: both converge to the tolerance and to
+    the same solution (fp32 summation order is the only difference)."""
+    out = {}
+    for spmv in ("rows", "stream"):
+        field, svh, osvh, feats, xyz, nxyz, nval, (pw, nw, rw) = _solve_setup(cuda)
+        field.solver_config.update(tol=1e-6, max_iter=3000, spmv=spmv)
+        t = lambda a: torch.from_numpy(a).to(cuda)
+        field.solve(t(xyz), t(nxyz), t(nval), pw, nw, rw)
+        assert field.solve_info["converged"] and field.solve_info["relative_residual"] <= 1e-6
+        out[spmv] = (_np(field.alpha).astype(np.float64), field.solve_info["iterations"])
+    (a_r, it_r), (a_s, it_s) = out["rows"], out["stream"]
+    assert abs(it_r - it_s) <= 0.1 * it_r + 3
+    assert np.linalg.norm(a_r - a_s) <= 1e-3 * np.linalg.norm(a_r)
 
 
 @pytest.mark.parametrize("C,approx", [(4, False), (16, True)])

@@ -111,7 +111,7 @@ def test_reconstructor_matches_oracle_pipeline(cuda):
         assert np.array_equal(_np(field.svh.keys[l]), osvh.keys(l))
         z = _np(field.z[l])
         assert np.abs(z - ref["feats"][l]).max() <= 1e-4 * np.abs(ref["feats"][l]).max(), f"features level {l}"
-    assert field.solve_info["n"] == ref["system"].n and field.solve_info["nnz"] == ref["system"].nnz or True
+    assert field.solve_info["n"] == ref["system"].n and field.solve_info["nnz"] == ref["system"].nnz
     # same field: values and gradients at the input points and around them
     rng = np.random.default_rng(5)
     q = np.concatenate([xyz[:5000], xyz[5000:10000] + rng.normal(size=(5000, 3)).astype(np.float32) * np.float32(W)])
@@ -122,4 +122,6 @@ def test_reconstructor_matches_oracle_pipeline(cuda):
     assert np.abs(_np(r.gradient) - go).max() <= 2e-2 * np.abs(go).max()
     # the reference's own training checks on the solved field (models/loss.py:188-198): |f| small at the
     # points, gradient along the (estimated) outward direction
-    assert np.abs(_np(r.value[:5000])).mean() <= 0.05 * fs
+    # (a sanity bound on the fit, not a parity bound: the oracle's own field sits at the same level)
+    assert np.abs(_np(r.value[:5000])).mean() <= 0.1 * fs
+    assert abs(np.abs(_np(r.value[:5000])).mean() - np.abs(fo[:5000]).mean()) <= 0.02 * fs
