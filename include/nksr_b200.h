@@ -299,6 +299,16 @@ NKSR_API int nksr_knn_normals(const nksr_svh_t* svh, const float* xyz, const flo
                      const int32_t* range, int64_t m, int k, float cos_min, float* normal, int32_t* keep,
                      float* eig, int32_t* inexact, void* stream);
 
+/* ---- f3: nksr.fields.PCNNField (examples/recons_colored_mesh.py:28-31): nearest data point of m query positions on
+ * the same multi-level voxel hash (svh / range as for nksr_knn_normals; xyz = the Morton-sorted cloud; origin3 = HOST
+ * float[3], the shift that was applied to the cloud before keying).  out_idx[i] = index (sorted order) of the nearest
+ * point (-1 only for an empty cloud); out_d2 (nullable) its squared distance.  A level's answer is accepted when it
+ * lies within that level's cell size (then it is exact); a query further than the coarsest cell size from every
+ * point (never a mesh vertex) is answered by a scan of all n_pts points. */
+NKSR_API int nksr_nearest_point(const nksr_svh_t* svh, const float* xyz, const int32_t* range, int64_t n_pts,
+                       const float* query, int64_t m, const float* origin3, int start_level, int32_t* out_idx,
+                       float* out_d2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,7 @@ _SIGNATURES = {
     "nksr_voxel_pca_normals": ("i", "ppqfpp"),
     "nksr_orient_normals": ("i", "ppppqfppp"),
     "nksr_knn_normals": ("i", "Spppp" + "qif" + "ppppp"),
+    "nksr_nearest_point": ("i", "Sppqpqpippp"),
 }
 
 _lib = None

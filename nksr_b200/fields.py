@@ -456,16 +456,33 @@ class SparseFeatureHierarchyCoords:
 
 
 class PCNNField:
-    """Nearest-neighbour colour texture (examples/recons_colored_mesh.py:28).  'Next' row f3 of
-    SURVEY section 8: chunked brute-force torch implementation, not a hot-path kernel yet."""
+    """Nearest-neighbour colour texture (examples/recons_colored_mesh.py:28-31): the colour
+    of a query is the colour of the nearest input point.  The cloud is hashed once (multi-level voxel hash of the
+    Morton-sorted points, shared with the kNN normal estimation); queries run one warp each in
+    csrc/nearest.cu (k_nearest_point) -- exact nearest neighbour, O(V log N) instead of the V x N distance matrix."""
+
+    START_LEVEL = 2       # cells of ~0.6 mean point spacings: the first level that usually holds the answer
 
     def __init__(self, xyz: torch.Tensor, color: torch.Tensor):
-        self.xyz, self.color = xyz, color
+        _lib.require_cuda(xyz, "xyz")
+        from .reconstructor import _knn_hash
+        xyz = xyz.detach().to(torch.float32).contiguous()
+        perm, self.svh, _, self.ranges, self.origin = _knn_hash(xyz)
+        self.xyz = xyz[perm].contiguous()
+        self.color = color.detach().to(xyz.device)[perm].contiguous()
+        self._origin_host = (C.c_float * 3)(*[float(v) for v in self.origin.tolist()])
+
+    def nearest(self, q: torch.Tensor):
+        """(index into the SORTED cloud, squared distance) of the nearest input point of every query"""
+        q = q.detach().to(self.xyz.device, torch.float32).contiguous()
+        m = q.shape[0]
+        idx = torch.empty(m, dtype=torch.int32, device=q.device)
+        d2 = torch.empty(m, dtype=torch.float32, device=q.device)
+        call("nksr_nearest_point", self.svh.view(), self.xyz, self.ranges, self.xyz.shape[0], q, m,
+             C.addressof(self._origin_host),
+             self.START_LEVEL, idx, d2, stream_ptr(q.device))
+        return idx, d2
 
     def evaluate_f(self, q: torch.Tensor, grad=False):
-        out = torch.empty((q.shape[0], self.color.shape[1]), device=q.device, dtype=self.color.dtype)
-        step = max(1, (1 << 24) // max(self.xyz.shape[0], 1))
-        for s in range(0, q.shape[0], step):
-            d = torch.cdist(q[s:s + step], self.xyz)
-            out[s:s + step] = self.color[d.argmin(dim=1)]
-        return EvaluationResult(value=out, gradient=None)
+        idx, _ = self.nearest(q)
+        return EvaluationResult(value=self.color[idx.long().clamp(min=0)], gradient=None)

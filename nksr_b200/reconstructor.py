@@ -61,7 +61,7 @@ KNN_LEVELS = 7        # levels of the voxel hash behind the kNN search (cell siz
 
 
 def _knn_hash(xyz: torch.Tensor, levels: int = KNN_LEVELS):
-    """Multi-level voxel hash of a cloud for neighbour searches: returns (perm, svh, base, ranges) with the points
+    """Multi-level voxel hash of a cloud for neighbour searches: returns (perm, svh, base, ranges, origin) with the points
     Morton-sorted by `perm`, the hierarchy of their containing voxels (finest cell ~ a sixth of the mean point
     spacing, doubling per level), base[l][i] = containing voxel of sorted point i, ranges[offset_l + v] = [first,
     last) sorted point of voxel v.  Keys are taken on coordinates shifted to the bounding-box corner."""
@@ -87,7 +87,7 @@ def _knn_hash(xyz: torch.Tensor, levels: int = KNN_LEVELS):
     ranges = torch.empty((svh.num_unknowns, 2), dtype=torch.int32, device=dev)
     for l in range(levels):
         call("nksr_row_ranges", base[l], n, ranges[offs[l]:], svh.num_voxels(l), st)
-    return perm, svh, base, ranges
+    return perm, svh, base, ranges, lo
 
 
 def estimate_normals_knn(xyz: torch.Tensor, sensor: Optional[torch.Tensor], knn: int = 64,
@@ -102,7 +102,7 @@ def estimate_normals_knn(xyz: torch.Tensor, sensor: Optional[torch.Tensor], knn:
     if k < 3:
         raise _lib.NksrError("normal estimation needs at least 3 points")
     dev, st = xyz.device, stream_ptr(xyz.device)
-    perm, svh, base, ranges = _knn_hash(xyz)
+    perm, svh, base, ranges, _ = _knn_hash(xyz)
     xs = xyz[perm].contiguous()
     ss = sensor.detach().to(torch.float32)[perm].contiguous() if sensor is not None else None
     nrm = torch.empty((n, 3), dtype=torch.float32, device=dev)

@@ -132,3 +132,35 @@ def test_preprocess_fn_contract(cuda):
         if r is not None and abs(float(np.dot(r, nn))) > 1 - 1e-5:
             hit += 1
     assert hit >= 0.97 * 4000
+
+
+@pytest.mark.parametrize("n_pts,n_q", [(200_000, 100_000), (500, 2000)])
+def test_pcnn_field_is_the_nearest_point(cuda, n_pts, n_q):
+    """PCNNField(xyz, color).evaluate_f(v) = colour of the nearest input point
+    (examples/recons_colored_mesh.py:28-31), the voxel-hash kernel against brute force on 1e5 queries: same minimum
+    distance everywhere, same colour except at exact distance ties."""
+    import nksr_b200
+    xyz, _, _ = scenes.crop("cfg4_outdoor", n_pts, with_sensor=True)
+    rng = np.random.default_rng(7)
+    col = rng.uniform(size=(n_pts, 3)).astype(np.float32)
+    # queries: near the surface (mesh-vertex like), plus some far away and some outside the bounding box
+    pick = rng.integers(0, n_pts, n_q)
+    q = xyz[pick] + rng.normal(size=(n_q, 3)).astype(np.float32) * 0.03
+    q[: n_q // 50] += rng.normal(size=(n_q // 50, 3)).astype(np.float32) * 3.0
+    q[n_q // 50: n_q // 25] += np.array([0.0, 0.0, 40.0], np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    tex = nksr_b200.fields.PCNNField(t(xyz), t(col))
+    out = tex.evaluate_f(t(q)).value
+    idx, d2 = tex.nearest(t(q))
+    assert out.shape == (n_q, 3) and int((idx < 0).sum()) == 0
+    # brute force in chunks (float32 differences, like the kernel)
+    X, Q = t(xyz), t(q)
+    best_d = torch.empty(n_q, device=cuda)
+    best_i = torch.empty(n_q, dtype=torch.long, device=cuda)
+    step = max(1, (1 << 26) // n_pts)
+    for s in range(0, n_q, step):
+        d = ((Q[s:s + step, None, :] - X[None, :, :]) ** 2).sum(-1)
+        best_d[s:s + step], best_i[s:s + step] = d.min(dim=1)
+    assert torch.allclose(d2, best_d, rtol=1e-5, atol=1e-12)
+    same = (out == t(col)[best_i]).all(dim=1)
+    assert same.float().mean().item() >= 0.9999
