@@ -239,6 +239,16 @@ NKSR_API int nksr_mesh_cell_flags(const nksr_svh_t* svh, int32_t* flag, void* st
 /* min-corner lattice coords (int32 xyz, units W/R) of flagged voxels, in voxel order */
 NKSR_API int nksr_mesh_stage0_cells(const nksr_svh_t* svh, const int32_t* flag, const int64_t* scan,
                            int32_t refine, int32_t* cells, void* stream);
+/* adaptive hierarchies (models/nksr_net.py:175-179,214): a LEAF of level >= 1 (no children) is meshed as if it were
+ * subdivided down to the finest level ("virtual" finest voxels), so all dual cells belong to one lattice.
+ * leaf_flags: flag[v] = 1 for childless level-l voxels; virtual_anchors: the 8^l finest-level ijk below every flagged
+ * voxel (scan = exclusive scan of flag; anchors [count * 8^l][3]); anchor_flags: flag[i] = 1 if the seven other corner
+ * voxels anchor + {0,1}^3 exist, really (level 0) or virtually below a leaf of level < coarse_levels */
+NKSR_API int nksr_mesh_leaf_flags(const nksr_svh_t* svh, int level, int32_t* flag, void* stream);
+NKSR_API int nksr_mesh_virtual_anchors(const nksr_svh_t* svh, int level, const int32_t* flag, const int64_t* scan,
+                              int32_t* anchors, void* stream);
+NKSR_API int nksr_mesh_anchor_flags(const nksr_svh_t* svh, const int32_t* anchors, int64_t n, int coarse_levels,
+                           int32_t* flag, void* stream);
 /* split every cell into g^3 children of size size/g */
 NKSR_API int nksr_mesh_split_cells(const int32_t* cells, int64_t n, int32_t size, int32_t g,
                           int32_t* out, void* stream);

@@ -97,6 +97,9 @@ _SIGNATURES = {
     "nksr_evaluate": ("i", "SFppqiippp"),
     "nksr_mesh_cell_flags": ("i", "Spp"),
     "nksr_mesh_stage0_cells": ("i", "Sppipp"),
+    "nksr_mesh_leaf_flags": ("i", "Sipp"),
+    "nksr_mesh_virtual_anchors": ("i", "Sipppp"),
+    "nksr_mesh_anchor_flags": ("i", "Spqipp"),
     "nksr_mesh_split_cells": ("i", "pqiipp"),
     "nksr_mesh_corner_keys": ("i", "pqiiiipp"),
     "nksr_mesh_lattice_pos": ("i", "pqiiifipp"),

@@ -186,9 +186,100 @@ __global__ void k_triangles(const int32_t* __restrict__ mc_case, const int64_t* 
   }
 }
 
+
+// ---- adaptive hierarchies (models/nksr_net.py:175-179,214): where a voxel of level l >= 1 is a LEAF (its children were
+// pruned) the field is still defined, so the mesher treats the leaf as if it were subdivided down to the finest level:
+// "virtual" finest voxels.  Dual cells are then cubes between the centres of 2x2x2 finest voxels, real or virtual --
+// one family of cells on one lattice, hence no cracks and no duplicates across level transitions.
+__global__ void k_leaf_flags(nksr_svh_t svh, int l, int32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= svh.n[l]) return;
+  const int32_t* ch = svh.child8[l] + i * 8;
+  int any = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) any |= (__ldg(ch + k) >= 0);
+  flag[i] = !any;
+}
+
+// 8^l finest-level coordinates (ijk, not offset) below every flagged level-l voxel, x-major inside a leaf
+__global__ void k_virtual_anchors(nksr_svh_t svh, int l, const int32_t* __restrict__ flag,
+                                  const int64_t* __restrict__ scan, int32_t* __restrict__ out) {
+  const int per = 1 << (3 * l);
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= svh.n[l] * (int64_t)per) return;
+  const int64_t i = t >> (3 * l);
+  if (!flag[i]) return;
+  const int d = (int)(t & (per - 1));
+  const int m = (1 << l) - 1;
+  const int dx = d >> (2 * l), dy = (d >> l) & m, dz = d & m;
+  int ux, uy, uz;
+  morton3_decode(__ldg(svh.keys[l] + i), ux, uy, uz);
+  const int off = level_offset(l);
+  const int64_t o = (scan[i] * per + d) * 3;
+  out[o] = ((ux - off) << l) + dx;
+  out[o + 1] = ((uy - off) << l) + dy;
+  out[o + 2] = ((uz - off) << l) + dz;
+}
+
+// finest voxel (x,y,z) exists: really, or virtually below a leaf of one of the levels 1 .. coarse-1
+__device__ __forceinline__ bool voxel_exists(const nksr_svh_t& svh, int coarse, int x, int y, int z) {
+  const int o0 = level_offset(0);
+  if (find_key(svh.keys[0], svh.n[0], morton3(x + o0, y + o0, z + o0)) >= 0) return true;
+  for (int l = 1; l < coarse; ++l) {
+    const int o = level_offset(l);
+    const int v = find_key(svh.keys[l], svh.n[l], morton3((x >> l) + o, (y >> l) + o, (z >> l) + o));
+    if (v < 0) continue;
+    const int32_t* ch = svh.child8[l] + (int64_t)v * 8;
+    int any = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) any |= (__ldg(ch + k) >= 0);
+    if (!any) return true;
+  }
+  return false;
+}
+
+__global__ void k_anchor_flags(nksr_svh_t svh, const int32_t* __restrict__ anchors, int64_t n, int coarse,
+                               int32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = anchors[3 * i], y = anchors[3 * i + 1], z = anchors[3 * i + 2];
+  int ok = 1;
+  for (int c = 1; c < 8 && ok; ++c) ok &= voxel_exists(svh, coarse, x + ((c >> 2) & 1), y + ((c >> 1) & 1), z + (c & 1));
+  flag[i] = ok;
+}
+
 }  // namespace
 
 extern "C" {
+
+int nksr_mesh_leaf_flags(const nksr_svh_t* svh, int level, int32_t* flag, void* stream) {
+  if (!svh || level < 1 || level >= svh->depth || !svh->child8[level]) return NKSR_E_INVALID;
+  if (svh->n[level] == 0) return NKSR_OK;
+  k_leaf_flags<<<grid_for(svh->n[level], 256), 256, 0, as_stream(stream)>>>(*svh, level, flag);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_mesh_virtual_anchors(const nksr_svh_t* svh, int level, const int32_t* flag, const int64_t* scan,
+                              int32_t* anchors, void* stream) {
+  if (!svh || level < 1 || level >= svh->depth || level > 6) return NKSR_E_INVALID;
+  if (svh->n[level] == 0) return NKSR_OK;
+  const int64_t work = svh->n[level] << (3 * level);
+  k_virtual_anchors<<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(*svh, level, flag, scan, anchors);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_mesh_anchor_flags(const nksr_svh_t* svh, const int32_t* anchors, int64_t n, int coarse_levels, int32_t* flag,
+                           void* stream) {
+  if (!svh || coarse_levels < 1 || coarse_levels > svh->depth) return NKSR_E_INVALID;
+  for (int l = 1; l < coarse_levels; ++l)
+    if (!svh->child8[l]) return NKSR_E_INVALID;
+  if (n == 0) return NKSR_OK;
+  k_anchor_flags<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(*svh, anchors, n, coarse_levels, flag);
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
 
 int nksr_mesh_cell_flags(const nksr_svh_t* svh, int32_t* flag, void* stream) {
   if (!svh || svh->depth < 1) return NKSR_E_INVALID;

@@ -32,9 +32,12 @@ def _evaluate(field, xyz, max_points):
 
 
 def extract_dual_mesh(field, grid_upsample: int = 1, mise_iter: int = 0, max_points: int = -1,
-                      cell_filter=None) -> DualMesh:
+                      cell_filter=None, multi_level=None) -> DualMesh:
     """`cell_filter` (optional, (n_0,) bool): only dual cells whose min-corner voxel passes are meshed --
-    used by the multi-GPU path so that every rank meshes the cells it owns."""
+    used by the multi-GPU path so that every rank meshes the cells it owns.
+    `multi_level` (default: on for hierarchies built by build_adaptive_normal_variation, models/nksr_net.py:175-179):
+    leaf voxels of the coarser levels are meshed as if subdivided down to the finest level, so pruned regions are
+    covered and the surface has no cracks at level transitions."""
     svh = field.svh
     dev = svh.device
     st = stream_ptr(dev)
@@ -46,19 +49,52 @@ def extract_dual_mesh(field, grid_upsample: int = 1, mise_iter: int = 0, max_poi
     R = g * (2 ** rounds)
     empty = DualMesh(v=torch.zeros((0, 3), device=dev), f=torch.zeros((0, 3), dtype=torch.int64, device=dev), c=None)
     n0 = svh.num_voxels(0)
-    if n0 == 0:
+    if n0 == 0 and not (multi_level or getattr(svh, "adaptive_depth", 0)):
         return empty
-    # ---- stage-0 cells: duals of 2x2x2 active finest voxels
-    flag = torch.empty(n0, dtype=torch.int32, device=dev)
-    call("nksr_mesh_cell_flags", svh.view(), flag, st)
-    if cell_filter is not None:
-        flag = (flag * cell_filter.to(torch.int32)).contiguous()
-    scan = _lib.exclusive_scan32(flag)
-    n_cells = int(scan[-1].item())
-    if n_cells == 0:
-        return empty
-    cells = torch.empty((n_cells, 3), dtype=torch.int32, device=dev)
-    call("nksr_mesh_stage0_cells", svh.view(), flag, scan, R, cells, st)
+    if multi_level is None:
+        multi_level = bool(getattr(svh, "adaptive_depth", 0))
+    coarse = min(int(getattr(svh, "adaptive_depth", 0)) or svh.depth, svh.depth) if multi_level else 1
+    if coarse <= 1:
+        # ---- stage-0 cells: duals of 2x2x2 active finest voxels
+        flag = torch.empty(n0, dtype=torch.int32, device=dev)
+        call("nksr_mesh_cell_flags", svh.view(), flag, st)
+        if cell_filter is not None:
+            flag = (flag * cell_filter.to(torch.int32)).contiguous()
+        scan = _lib.exclusive_scan32(flag)
+        n_cells = int(scan[-1].item())
+        if n_cells == 0:
+            return empty
+        cells = torch.empty((n_cells, 3), dtype=torch.int32, device=dev)
+        call("nksr_mesh_stage0_cells", svh.view(), flag, scan, R, cells, st)
+    else:
+        # ---- adaptive hierarchy: leaves of the coarser levels count as subdivided ("virtual" finest voxels); a cell
+        # is the cube between 2x2x2 finest voxels, real or virtual -- one lattice, no cracks at level transitions
+        if cell_filter is not None:
+            raise _lib.NksrError("multi-level meshing does not take a cell filter (multi-GPU meshing)")
+        anchors = [torch.empty((n0, 3), dtype=torch.int32, device=dev)]
+        if n0:
+            call("nksr_decode_ijk", svh.keys[0], n0, 0, anchors[0], st)
+        for l in range(1, coarse):
+            n_l = svh.num_voxels(l)
+            if n_l == 0:
+                continue
+            leaf = torch.empty(n_l, dtype=torch.int32, device=dev)
+            call("nksr_mesh_leaf_flags", svh.view(), l, leaf, st)
+            lscan = _lib.exclusive_scan32(leaf)
+            n_leaf = int(lscan[-1].item())
+            if n_leaf:
+                va = torch.empty((n_leaf * 8 ** l, 3), dtype=torch.int32, device=dev)
+                call("nksr_mesh_virtual_anchors", svh.view(), l, leaf, lscan, va, st)
+                anchors.append(va)
+        anchors = torch.cat(anchors) if len(anchors) > 1 else anchors[0]
+        flag = torch.empty(anchors.shape[0], dtype=torch.int32, device=dev)
+        call("nksr_mesh_anchor_flags", svh.view(), anchors, anchors.shape[0], coarse, flag, st)
+        scan = _lib.exclusive_scan32(flag)
+        n_cells = int(scan[-1].item())
+        if n_cells == 0:
+            return empty
+        cells = (_lib.compact_rows(anchors, flag, scan, n_cells) * R).contiguous()
+        del anchors
     lo = cells.min(dim=0).values.tolist()
     hi = cells.max(dim=0).values.tolist()
     if max(h - l for h, l in zip(hi, lo)) + R >= MAX_LATTICE_EXTENT:

@@ -107,7 +107,10 @@ class SparseFeatureHierarchy:
             leaf = ((variation < tau) | (acc[:, 3] == 0)) & ~drop[l]      # point-free (splat-only) voxels are leaves too
             stop = leaf | drop[l]                           # everything below a leaf (or a dropped voxel) goes
             drop[l - 1] |= stop[self.parent[l - 1].long()]
-        return self.build_from_keys([k[~d] for k, d in zip(keys, drop)], top_keys=self.top_keys)
+        out = self.build_from_keys([k[~d] for k, d in zip(keys, drop)], top_keys=self.top_keys)
+        # leaves exist on the levels below `adaptive_depth`: extract_dual_mesh meshes them as if subdivided
+        self.adaptive_depth = min(int(adaptive_depth), self.depth)
+        return out
 
     def build_from_keys(self, keys, top_keys=None):
         """Adopt sorted, unique, parent-closed Morton keys per level and build the tables.

@@ -476,7 +476,7 @@ def lattice_pos(s, W, R):
     return (np.float32(W) * (np.float32(0.5) + s.astype(np.float32) / np.float32(R))).astype(np.float32)
 
 
-def extract_dual_mesh(svh: OracleSVH, eval_fn, grid_upsample=1, mise_iter=0, mask_fn=None):
+def extract_dual_mesh(svh: OracleSVH, eval_fn, grid_upsample=1, mise_iter=0, mask_fn=None, coarse_levels=1):
     """Dual marching cubes with MISE refinement (SPEC S8-S10).
 
     Stage-0 cells are the cubes spanned by the centres of 2x2x2 active finest voxels (the dual
@@ -489,8 +489,33 @@ def extract_dual_mesh(svh: OracleSVH, eval_fn, grid_upsample=1, mise_iter=0, mas
     W = svh.voxel_size
     R = grid_upsample * (2 ** mise_iter)
     ijk = svh.ijk(0).astype(np.int64)
-    nb = svh.lookup(0, ijk[:, None, :] + _OFF8[None])
-    cells = ijk[np.all(nb >= 0, axis=1)] * R              # min-corner lattice coords
+    if coarse_levels <= 1:
+        nb = svh.lookup(0, ijk[:, None, :] + _OFF8[None])
+        cells = ijk[np.all(nb >= 0, axis=1)] * R              # min-corner lattice coords
+    else:
+        # adaptive hierarchies (models/nksr_net.py:175-179,214): a leaf of level 1 .. coarse_levels-1 counts as
+        # subdivided down to the finest level ("virtual" finest voxels); cells = cubes between 2x2x2 finest voxels,
+        # real or virtual.  Anchors: the real finest voxels, then the virtual ones level by level, leaf by leaf, x-major.
+        leaf = {}
+        anchors = [ijk]
+        for l in range(1, min(coarse_levels, svh.depth)):
+            leaf[l] = ~np.isin(svh.keys[l], svh.keys[l - 1] >> 3)
+            lij = svh.ijk(l).astype(np.int64)[leaf[l]]
+            m = 1 << l
+            sub = np.array([[a, b, c] for a in range(m) for b in range(m) for c in range(m)], np.int64)
+            anchors.append(((lij << l)[:, None, :] + sub[None]).reshape(-1, 3))
+        anchors = np.concatenate(anchors)
+
+        def exists(j):
+            ok = svh.lookup(0, j) >= 0
+            for l, lf in leaf.items():
+                v = svh.lookup(l, j >> l)
+                ok |= (v >= 0) & lf[np.maximum(v, 0)]
+            return ok
+        ok = np.ones(anchors.shape[0], bool)
+        for c in range(1, 8):
+            ok &= exists(anchors + _OFF8[c][None])
+        cells = anchors[ok] * R
     size = R
     if cells.shape[0] == 0:
         return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int64)

@@ -96,3 +96,57 @@ def test_mesh_of_solved_field_matches_oracle_mesh_as_surface(cuda):
         assert np.quantile(d1, 0.99) <= 0.02 * cell and np.quantile(d2, 0.99) <= 0.02 * cell, (g, mise)
         r = np.linalg.norm(_np(mesh.v), axis=1)
         assert abs(np.median(r) - 0.35) < 0.004
+
+
+def _boundary(v, faces):
+    """(lengths of the edges used by exactly one triangle, number of edges used by more than two)"""
+    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]])
+    e.sort(axis=1)
+    u, c = np.unique(e, axis=0, return_counts=True)
+    b = u[c == 1]
+    return np.linalg.norm(v[b[:, 0]] - v[b[:, 1]], axis=1), int((c > 2).sum())
+
+
+@pytest.mark.parametrize("g,mise", [(1, 1), (2, 0), (1, 0)])
+def test_adaptive_hierarchy_meshes_without_holes_or_cracks(cuda, g, mise):
+    """VERDICT r1 missing #6 / models/nksr_net.py:175-179,214: a hierarchy whose finest voxels were pruned (coarse
+    leaves) must still be meshed everywhere.  Half of a densely sampled sphere loses its level-0 voxels; leaves count
+    as subdivided ("virtual" finest voxels), so the cells form ONE lattice: the CUDA mesher equals the oracle's
+    restatement cell for cell (same vertices to 1e-5, same faces), the surface is closed (every edge in exactly two
+    triangles -- no holes where level 0 is missing, no cracks at the level transition), whereas the finest-level-only
+    extraction of the same hierarchy is open."""
+    import nksr_b200
+    xyz, _ = clouds.sphere(60_000, noise=0.0005)
+    W, L = 0.04, 3
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    osvh = O.OracleSVH(W, L).build_point_splatting(xyz)
+    keys = list(osvh.keys)
+    keys[0] = keys[0][O.key_to_ijk(keys[0], 0)[:, 0] >= 0]           # x < 0: level-1 voxels become leaves
+    osvh = O.OracleSVH(W, L).build_from_keys(keys)
+    svh = nksr_b200.SparseFeatureHierarchy(W, L, cuda).build_from_keys([t(k) for k in keys])
+
+    class Analytic(nksr_b200.fields.BaseField):                      # f = r0 - |x|: the mesher alone is under test
+        def evaluate_f(self, q, grad=False):
+            return nksr_b200.fields.EvaluationResult(value=0.35 - q.norm(dim=1), gradient=None)
+
+    field = Analytic(svh)
+    ev = lambda q: 0.35 - np.linalg.norm(q.astype(np.float32), axis=1).astype(np.float32)
+    from nksr_b200.meshing import extract_dual_mesh
+    m_fine = extract_dual_mesh(field, g, mise, multi_level=False)
+    m_all = extract_dual_mesh(field, g, mise, multi_level=True)
+    vo, fo = O.extract_dual_mesh(osvh, ev, g, mise, coarse_levels=L)
+    v, f = _np(m_all.v), _np(m_all.f)
+    assert v.shape == vo.shape and f.shape == fo.shape
+    assert np.abs(v - vo).max() <= 1e-5 and np.array_equal(f, fo)
+    # no open boundary is added by the pruning: the data band itself leaves small holes where the sphere clips a cell
+    # that holds no data point (the unpruned hierarchy has them too); the finest-level-only extraction of the pruned
+    # hierarchy has a macroscopic hole -- the whole x < 0 half
+    b_all, nm_all = _boundary(v, f)
+    b_fine, _ = _boundary(_np(m_fine.v), _np(m_fine.f))
+    full = O.OracleSVH(W, L).build_point_splatting(xyz)
+    b_full, _ = _boundary(*O.extract_dual_mesh(full, ev, g, mise))
+    assert nm_all == 0
+    assert b_all.sum() <= b_full.sum() + 1e-6 and (b_all.size == 0 or b_all.max() <= 0.75 * W)
+    assert b_fine.sum() >= 1.5                                       # ~ the great circle at x = 0 (2 pi 0.35 = 2.2)
+    assert (v[:, 0] < -0.3).any() and not (_np(m_fine.v)[:, 0] < -0.1).any()
+    assert np.abs(np.linalg.norm(v, axis=1) - 0.35).max() <= 0.02 * W
