@@ -150,6 +150,8 @@ class KernelField(BaseField):
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         hk = torch.empty(m, dtype=torch.int64, device=dev)
         call("nksr_point_half_keys", xyz, m, svh.voxel_size, hk, status, st)
+        if int(status.item()) & 1:
+            raise _lib.NksrError("constraint locations outside the supported range (|x| < 2^19 voxels) or non-finite")
         _, perm = _lib.sort_pairs(hk, torch.arange(m, dtype=torch.int32, device=dev))
         perm = perm.long()
         xs = xyz[perm].contiguous()

@@ -36,7 +36,12 @@ def _count_voxels(xyz: torch.Tensor, w: float) -> int:
     hk = torch.empty(n, dtype=torch.int64, device=xyz.device)
     status = torch.zeros(1, dtype=torch.int32, device=xyz.device)
     call("nksr_point_half_keys", xyz, n, float(w), hk, status, stream_ptr(xyz.device))
-    return int(_lib.unique_sorted(_lib.sort_keys(hk), 3).numel())
+    count = int(_lib.unique_sorted(_lib.sort_keys(hk), 3).numel())
+    if int(status.item()) & 1:
+        # |x| / w outside the 2^19-voxel key range: keys collapse; report "finer than representable" so that the
+        # bisections that call this move towards larger voxels
+        return n
+    return count
 
 
 def voxel_size_from_detail(xyz: torch.Tensor, detail_level: float) -> float:
