@@ -109,6 +109,12 @@ NKSR_API int nksr_row_ranges(const int32_t* base_l, int64_t m, int32_t* range, i
 NKSR_API int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* xyz,
                     const int32_t* base, int64_t m, int mode, int approx_kernel_grad, float* e,
                     void* stream);
+/* the same rows, bitwise, built one warp per VOXEL: range = nksr_row_ranges of every level (concatenated in level
+ * order) of the Morton-SORTED locations xyz; stencil and features are fetched once per voxel.  channels in {4, 8, 16},
+ * otherwise NKSR_E_INVALID (callers then use nksr_build_rows) */
+NKSR_API int nksr_build_rows_voxel(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* xyz,
+                          const int32_t* base, const int32_t* range, int64_t m, int mode, int approx_kernel_grad,
+                          float* e, void* stream);
 /* structural row lengths of A: cnt[i] (same + coarser levels), cnt_down[i] (finer levels) */
 NKSR_API int nksr_gram_count(const nksr_svh_t* svh, int32_t* cnt, int32_t* cnt_down, void* stream);
 NKSR_API size_t nksr_scan_workspace_bytes(int64_t n);

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "nksr_pool27": ("i", "ppqipp"),
     "nksr_pool_children": ("i", "ppqipp"),
     "nksr_build_rows": ("i", "SFppqiipp"),
+    "nksr_build_rows_voxel": ("i", "SFpppqiipp"),
     "nksr_gram_count": ("i", "Sppp"),
     "nksr_scan_workspace_bytes": ("z", "q"),
     "nksr_gram_rowptr": ("i", "ppqppzp"),

@@ -60,6 +60,100 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
   }
 }
 
+// ---- kernel rows, one warp per VOXEL (the default): all locations whose containing voxel on level l is u share u's
+// 27-stencil and its features, and they are contiguous (locations are Morton sorted).  The warp-per-location kernel
+// above re-gathers 27 feature rows per location and level -- 27 L1 wavefronts per channel load, the measured limit of
+// that kernel (r2b: ~110 cycles per (location, level) and SM); here the stencil and the features (C <= 16, as float4
+// registers) are fetched ONCE per voxel and the loop over the voxel's locations is ALU + shuffles + the row stores.
+// Same arithmetic, same order: bitwise the rows of k_build_rows.
+template <int MODE, int NC4>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_build_rows_voxel(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, const int32_t* __restrict__ range,
+                   int l, bool fullgrad, float* __restrict__ e) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  if (u >= svh.n[l]) return;
+  const int2 r = __ldg(reinterpret_cast<const int2*>(range) + svh.offset[l] + u);
+  if (r.x >= r.y) return;
+  constexpr bool GRAD = MODE == 1;
+  constexpr int ROWS = GRAD ? 3 : 1;
+  int ux, uy, uz;
+  morton3_decode(__ldg(svh.keys[l] + u), ux, uy, uz);
+  const int nb = lane < 27 ? __ldg(svh.nbr27[l] + u * 27 + lane) : -1;
+  const bool ok = nb >= 0;
+  float zc[NC4 * 4];
+#pragma unroll
+  for (int q = 0; q < NC4; ++q) {
+    const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(feat.z[l] + (int64_t)nb * (NC4 * 4)) + q)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    zc[4 * q] = v.x; zc[4 * q + 1] = v.y; zc[4 * q + 2] = v.z; zc[4 * q + 3] = v.w;
+  }
+  int dx, dy, dz;
+  slot_to_d(lane < 27 ? lane : 13, dx, dy, dz);
+  const int off = level_offset(l);
+  const double inv = (1.0 / (double)svh.voxel_size) * (1.0 / (double)(1 << l));
+  const double cx = (double)(ux - off) + 0.5, cy = (double)(uy - off) + 0.5, cz = (double)(uz - off) + 0.5;
+  const float iw = 1.f / (svh.voxel_size * (float)(1 << l));
+  const int L = svh.depth;
+  for (int q = r.x; q < r.y; ++q) {
+    const float px = __ldg(xyz + 3 * (int64_t)q), py = __ldg(xyz + 3 * (int64_t)q + 1), pz = __ldg(xyz + 3 * (int64_t)q + 2);
+    const float tx = (float)((double)px * inv - cx), ty = (float)((double)py * inv - cy),
+                tz = (float)((double)pz * inv - cz);
+    float bx, dbx, ttx, dtx, by, dby, tty, dty, bz, dbz, ttz, dtz;
+    axis_weights(tx, dx, bx, dbx, ttx, dtx);
+    axis_weights(ty, dy, by, dby, tty, dty);
+    axis_weights(tz, dz, bz, dbz, ttz, dtz);
+    const float B3 = bx * by * bz;
+    const float T3 = ok ? ttx * tty * ttz : 0.f;
+    float dT3[3] = {0.f, 0.f, 0.f};
+    if (GRAD) {
+      dT3[0] = ok ? dtx * tty * ttz : 0.f;
+      dT3[1] = ok ? ttx * dty * ttz : 0.f;
+      dT3[2] = ok ? ttx * tty * dtz : 0.f;
+    }
+    float dot = 0.f, ddot[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < NC4 * 4; ++c) {
+      const float phi = warp_sum(T3 * zc[c]);
+      dot = fmaf(phi, zc[c], dot);
+      if (GRAD && fullgrad) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float dphi = warp_sum(dT3[a] * zc[c]);
+          ddot[a] = fmaf(dphi, zc[c], ddot[a]);
+        }
+      }
+    }
+    float* out = e + ((int64_t)q * L + l) * ROWS * NKSR_ROW_STRIDE;
+    if (GRAD) {
+      out[lane] = ok ? (dbx * by * bz * dot + B3 * ddot[0]) * iw : 0.f;
+      out[32 + lane] = ok ? (bx * dby * bz * dot + B3 * ddot[1]) * iw : 0.f;
+      out[64 + lane] = ok ? (bx * by * dbz * dot + B3 * ddot[2]) * iw : 0.f;
+    } else if (MODE == 2) {
+      const float tau = lane == 27 ? tx : (lane == 28 ? ty : tz);
+      out[lane] = lane < 27 ? (ok ? dot : 0.f) : (lane < 30 ? tau : 0.f);
+    } else {
+      out[lane] = ok ? B3 * dot : 0.f;
+    }
+  }
+}
+
+// locations whose containing voxel on some level is inactive (e.g. the centre of a childless voxel on the level
+// below): their lines of that level are zero
+template <int ROWS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_zero_inactive_rows(int depth, const int32_t* __restrict__ base, int64_t m, float* __restrict__ e) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= m) return;
+  for (int l = 0; l < depth; ++l) {
+    if (__ldg(base + (int64_t)l * m + i) >= 0) continue;
+    float* out = e + ((int64_t)i * depth + l) * ROWS * NKSR_ROW_STRIDE;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) out[r * 32 + lane] = 0.f;
+  }
+}
+
 // one warp per query: f(x) = sum_l sum_s alpha * K ; containing voxels found by top search + descent
 template <bool GRAD>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -163,6 +257,35 @@ int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float*
     else NKSR_ROWS(2, NKSR_MAX_DEPTH);
   }
 #undef NKSR_ROWS
+  NKSR_CHECK_LAUNCH();
+  return NKSR_OK;
+}
+
+int nksr_build_rows_voxel(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* xyz, const int32_t* base,
+                          const int32_t* range, int64_t m, int mode, int approx_kernel_grad, float* e, void* stream) {
+  if (!svh || !feat || !range || svh->depth < 1 || svh->depth > NKSR_MAX_DEPTH) return NKSR_E_INVALID;
+  if (mode < 0 || mode > 2 || (mode == 2 && !approx_kernel_grad)) return NKSR_E_INVALID;
+  const int C = feat->channels;
+  if (C != 4 && C != 8 && C != 16) return NKSR_E_INVALID;     // features are held as float4 registers
+  if (m == 0) return NKSR_OK;
+  cudaStream_t s = as_stream(stream);
+  const bool full = mode == 1 && !approx_kernel_grad;
+  const int zgrid = grid_for(m, kWarpsPerBlock);
+  if (mode == 1) k_zero_inactive_rows<3><<<zgrid, kWarpsPerBlock * 32, 0, s>>>(svh->depth, base, m, e);
+  else k_zero_inactive_rows<1><<<zgrid, kWarpsPerBlock * 32, 0, s>>>(svh->depth, base, m, e);
+  for (int l = 0; l < svh->depth; ++l) {
+    if (svh->n[l] == 0) continue;
+    const int grid = grid_for(svh->n[l], kWarpsPerBlock);
+#define NKSR_VROWS(MODE, NC4) \
+  k_build_rows_voxel<MODE, NC4><<<grid, kWarpsPerBlock * 32, 0, s>>>(*svh, *feat, xyz, range, l, full, e)
+#define NKSR_VROWS_C(MODE)                                                     \
+  do {                                                                         \
+    if (C == 4) NKSR_VROWS(MODE, 1); else if (C == 8) NKSR_VROWS(MODE, 2); else NKSR_VROWS(MODE, 4); \
+  } while (0)
+    if (mode == 0) NKSR_VROWS_C(0); else if (mode == 1) NKSR_VROWS_C(1); else NKSR_VROWS_C(2);
+#undef NKSR_VROWS_C
+#undef NKSR_VROWS
+  }
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

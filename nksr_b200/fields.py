@@ -164,8 +164,15 @@ class KernelField(BaseField):
             call("nksr_row_ranges", base[l], m, ranges[offs[l]:], svh.num_voxels(l), st)
         width = _lib.ROW_STRIDE * (3 if mode == 1 else 1)
         e = torch.empty((m, svh.depth, width), dtype=torch.float32, device=dev)      # location-major
-        call("nksr_build_rows", svh.view(), self.feat_view(), xs, base, m, mode,
-             int(self.approx_kernel_grad), e, st)
+        # 'voxel' (default): one warp per voxel, stencil + features fetched once for all the voxel's locations;
+        # 'location': one warp per location (any channel count)
+        rows = self.solver_config.get("rows") or os.environ.get("NKSR_ROWS") or "voxel"
+        if rows == "voxel" and self.z[0].shape[1] in (4, 8, 16):
+            call("nksr_build_rows_voxel", svh.view(), self.feat_view(), xs, base, ranges, m, mode,
+                 int(self.approx_kernel_grad), e, st)
+        else:
+            call("nksr_build_rows", svh.view(), self.feat_view(), xs, base, m, mode,
+                 int(self.approx_kernel_grad), e, st)
         return xs, ex, base, ranges, e
 
     def solve(self, pos_xyz, normal_xyz=None, normal_value=None, pos_weight=1.0, normal_weight=1.0,
@@ -238,7 +245,10 @@ class KernelField(BaseField):
             # compact gradient rows (one line instead of three per location and level) save 2/3 of
             # the row memory but cost ALU in the assembly; measured slower on B200 (profiles/r1c),
             # so they are opt-in for clouds that would not fit otherwise
-            nrm_mode = 2 if (self.approx_kernel_grad and self.solver_config.get("compact_rows", False)) else 1
+            compact = self.solver_config.get("compact_rows")
+            if compact is None:
+                compact = os.environ.get("NKSR_COMPACT_ROWS", "0") == "1"
+            nrm_mode = 2 if (self.approx_kernel_grad and compact) else 1
             _, t_nrm, _, range_nrm, e_nrm = self._sorted_rows(normal_xyz, nrm_mode, normal_value)
             cs.nrm_compact = int(nrm_mode == 2)
             keep += [t_nrm, range_nrm, e_nrm]

@@ -92,6 +92,28 @@ def test_kernel_rows_match_oracle(cuda, C, approx):
             assert np.all(e_np[:, l].reshape(-1, 32)[:, 27:] == 0)
 
 
+@pytest.mark.parametrize("C,approx,mode", [(4, False, 0), (4, False, 1), (4, True, 1), (4, True, 2), (16, False, 1),
+                                           (8, True, 2), (16, False, 0)])
+def test_voxel_rows_are_the_location_rows(cuda, C, approx, mode):
+    """csrc/field.cu: the warp-per-voxel row builder (default; stencil + features fetched once per voxel) writes
+    bitwise the rows of the warp-per-location builder -- including the zero lines of locations whose containing
+    voxel is inactive on some level (here: constraint locations at the centres of childless level-1 voxels)."""
+    xyz, _ = clouds.shapenet_like(3000)
+    svh, osvh = _build(cuda, xyz, 0.02, 4)
+    feats = _feats(osvh, C, 7)
+    rng = np.random.default_rng(4)
+    q = np.concatenate([xyz[:2000], osvh.centers(1), osvh.centers(0)[:3000] + rng.uniform(-0.4, 0.4, (3000, 3)).astype(np.float32) * 0.02])
+    q = torch.from_numpy(np.ascontiguousarray(q.astype(np.float32))).to(cuda)
+    out = {}
+    for rows in ("location", "voxel"):
+        field = _field(cuda, svh, feats, approx)
+        field.solver_config["rows"] = rows
+        _, _, base, _, e = field._sorted_rows(q, mode)
+        out[rows] = _np(e).copy()
+    assert (_np(base) < 0).any()                                      # the zero-line case is exercised
+    assert np.array_equal(out["location"], out["voxel"])
+
+
 def _solve_setup(cuda, C=4, approx=False, n_pts=3000, W=0.02, L=4, cloud="shapenet"):
     xyz, nrm = clouds.shapenet_like(n_pts) if cloud == "shapenet" else clouds.sphere(n_pts)
     svh, osvh = _build(cuda, xyz, W, L)
