@@ -157,24 +157,28 @@ k_place_prefix(nksr_svh_t svh, int l, int k, const int32_t* __restrict__ class_c
 //   M[si][s] = sum_rows w * E_l[row][si] * E_{l+k}[row][s]      (27 x 27, lane s keeps column s)
 // ONCE, instead of each of the 27 matrix rows around u streaming all of u's constraint rows again.
 // Block layout: 28 lines of 32 floats -- lines 0..26 = M[si][:], line 27 = rhs share per si (k = 0).
-// m[s] += el[lane s] * ek for the 27 stencil slots s: 27 shuffles feeding 14 packed FFMA2 (sm_100)
-__device__ __forceinline__ void gram_block_update(float (&m)[28], float el, float ek) {
+// m[s] += el[s] * ek for the 27 stencil slots s (lane = column of the block, m[s] = row s): the weighted level-l line
+// `el` of the constraint row is staged in shared memory and read back as seven broadcast 128-bit loads feeding 14 packed
+// FFMA2 (sm_100) -- the first version fetched the 28 values with 28 shuffles per row, two thirds of its instructions
+__device__ __forceinline__ void gram_block_update(float (&m)[28], const float* __restrict__ el_line, float ek) {
   const float2 ek2 = make_float2(ek, ek);
+  const float4* l4 = reinterpret_cast<const float4*>(el_line);
 #pragma unroll
-  for (int s = 0; s < 28; s += 2) {
-    const float a0 = __shfl_sync(0xffffffffu, el, s);
-    const float a1 = __shfl_sync(0xffffffffu, el, s + 1);      // slot 27 is padding (zero)
-    const float2 acc = __ffma2_rn(make_float2(a0, a1), ek2, make_float2(m[s], m[s + 1]));
-    m[s] = acc.x;
-    m[s + 1] = acc.y;
+  for (int j = 0; j < 7; ++j) {
+    const float4 a = l4[j];                                    // slot 27 is padding (zero)
+    const float2 r0 = __ffma2_rn(make_float2(a.x, a.y), ek2, make_float2(m[4 * j], m[4 * j + 1]));
+    const float2 r1 = __ffma2_rn(make_float2(a.z, a.w), ek2, make_float2(m[4 * j + 2], m[4 * j + 3]));
+    m[4 * j] = r0.x; m[4 * j + 1] = r0.y; m[4 * j + 2] = r1.x; m[4 * j + 3] = r1.y;
   }
 }
 
 template <int MAXL>
 __global__ void __launch_bounds__(kWarps * 32)
 k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks) {
+  __shared__ __align__(16) float stage[kWarps][3][32];
   const int lane = threadIdx.x & 31;
-  int64_t w = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  const int wid = threadIdx.x >> 5;
+  int64_t w = blockIdx.x * (int64_t)kWarps + wid;
   int l = cs.split_level;
   while (l < svh.depth && w >= svh.n[l] * (svh.depth - l)) { w -= svh.n[l] * (svh.depth - l); ++l; }
   if (l >= svh.depth) return;
@@ -191,9 +195,11 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
     for (int q = pb; q < pe; ++q) {
       const float* p0 = cs.e_pos + ((int64_t)q * L + l) * NKSR_ROW_STRIDE + lane;
       const float e0 = __ldg(p0);
-      const float el = cs.w_pos * e0;
       const float ek = k == 0 ? e0 : __ldg(p0 + k * NKSR_ROW_STRIDE);
-      gram_block_update(m, el, ek);
+      stage[wid][0][lane] = cs.w_pos * e0;
+      __syncwarp();
+      gram_block_update(m, stage[wid][0], ek);
+      __syncwarp();
     }
   }
   if (cs.range_nrm) {
@@ -201,14 +207,19 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
     const int nb = __ldg(rn), ne = __ldg(rn + 1);
     for (int q = nb; q < ne; ++q) {
       const float* p0 = cs.e_nrm + ((int64_t)q * L + l) * (3 * NKSR_ROW_STRIDE) + lane;
+      float ek[3];
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) {
         const float e0 = __ldg(p0 + ax * NKSR_ROW_STRIDE);
         const float el = cs.w_nrm * e0;
-        const float ek = k == 0 ? e0 : __ldg(p0 + (k * 3 + ax) * NKSR_ROW_STRIDE);
+        ek[ax] = k == 0 ? e0 : __ldg(p0 + (k * 3 + ax) * NKSR_ROW_STRIDE);
         if (k == 0) bvec = fmaf(el, __ldg(cs.t_nrm + (int64_t)q * 3 + ax), bvec);
-        gram_block_update(m, el, ek);
+        stage[wid][ax][lane] = el;
       }
+      __syncwarp();
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) gram_block_update(m, stage[wid][ax], ek[ax]);
+      __syncwarp();
     }
   }
   float* blk = mblocks + (cs.mblock_off[l] + (int64_t)u * nlev + k) * kBlockFloats;
