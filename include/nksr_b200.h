@@ -325,6 +325,22 @@ NKSR_API int nksr_nearest_point(const nksr_svh_t* svh, const float* xyz, const i
                        const float* query, int64_t m, const float* origin3, int start_level, int32_t* out_idx,
                        float* out_d2, void* stream);
 
+/* ---- f4: the reference's GT-SDF generator ext.sdfgen.sdf_from_points(queries, ref_xyz, ref_normal, nb_points, stdv,
+ * compute_grad, imls, adaptive_knn) (ext/sdfgen/sdf_from_points.cu:150-235 + ext/common/kdtree_cuda.cu; call sites
+ * dataset/av_gt_geometry.py:63-78, models/loss.py:85).  The reference points live in the same multi-level voxel hash
+ * (svh / range / origin3 as for nksr_nearest_point; xyz, normal, ref_std in the Morton-sorted order); search and vote
+ * are one kernel.  nksr_knn_mean_distance: out[i] = mean distance from query i to its k nearest reference points
+ * (queries = the reference points themselves gives the adaptive ref_std of sdf_from_points.cu:158-166).
+ * nksr_sdf_from_points: imls = 0: nearest-neighbour distance / point-to-plane distance with a majority vote for the
+ * sign (:92-147), imls = 1: the IMLS average (:33-90); grad nullable; nb_points, k <= 64. */
+NKSR_API int nksr_knn_mean_distance(const nksr_svh_t* svh, const float* xyz, const int32_t* range, int64_t n_pts,
+                           const float* origin3, const float* query, int64_t m, int k, int start_level,
+                           float* out, void* stream);
+NKSR_API int nksr_sdf_from_points(const nksr_svh_t* svh, const float* xyz, const float* normal, const float* ref_std,
+                         const int32_t* range, int64_t n_pts, const float* origin3, const float* query, int64_t m,
+                         int nb_points, float stdv, int imls, int start_level, float* sdf, float* grad,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ All arithmetic of the hot path runs in hand-written sm_100a CUDA kernels behind 
 include/nksr_b200.h (nksr_b200/libnksr_b200.so); there is no CPU or PyTorch fallback.
 Inference only: the solve is not differentiable (the reference needs that for training only).
 """
-from . import _lib, fields, meshing, network, svh  # noqa: F401
+from . import _lib, fields, meshing, network, sdfgen, svh  # noqa: F401
 from .fields import KernelField, LayerField, NeuralField, PCNNField  # noqa: F401
 from .network import NKSRNetwork, load_checkpoint_from_url  # noqa: F401
 from .reconstructor import Reconstructor, get_estimate_normal_preprocess_fn  # noqa: F401

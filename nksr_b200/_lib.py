@@ -118,6 +118,8 @@ _SIGNATURES = {
     "nksr_orient_normals": ("i", "ppppqfppp"),
     "nksr_knn_normals": ("i", "Spppp" + "qif" + "ppppp"),
     "nksr_nearest_point": ("i", "Sppqpqpippp"),
+    "nksr_knn_mean_distance": ("i", "Sppqppqiipp"),
+    "nksr_sdf_from_points": ("i", "Sppppqppqifiippp"),
 }
 
 _lib = None

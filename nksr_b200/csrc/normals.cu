@@ -3,7 +3,7 @@
 // the open CPU twin it follows is examples/recons_waymo_cpu.py:21-41 (kNN-PCA normal, flip to the
 // sensor side, drop grazing points).  Neighbourhood = the 27 voxels around the point's voxel of
 // a single-level hierarchy sized to hold ~knn points, instead of an exact kNN search.
-#include "common.cuh"
+#include "knn_common.cuh"
 
 namespace {
 
@@ -135,24 +135,6 @@ __global__ void k_orient_normals(const float* __restrict__ xyz, const float* __r
 // Then the 3 x 3 covariance of the k neighbours (self included) about their mean, its eigenvector of the smallest
 // eigenvalue (Jacobi, fp64), orientation to the sensor side and the grazing-angle flag.
 constexpr int kKnnWarps = 8;
-constexpr int kKnnBuf = 128;
-
-__device__ __forceinline__ void knn_sort128(unsigned long long* __restrict__ key, int lane) {
-  // ascending bitonic sort of 128 packed words by one warp
-  for (int k = 2; k <= kKnnBuf; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-      for (int q0 = 0; q0 < kKnnBuf / 2; q0 += 32) {
-        const int q = q0 + lane;
-        const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
-        const int hi = lo | j;
-        const unsigned long long a = key[lo], b = key[hi];
-        if ((a > b) == ((lo & k) == 0)) { key[lo] = b; key[hi] = a; }
-      }
-      __syncwarp();
-    }
-  }
-}
 
 __global__ void __launch_bounds__(kKnnWarps * 32)
 k_knn_normals(const nksr_svh_t svh, const float* __restrict__ xyz, const float* __restrict__ sensor,
@@ -166,7 +148,6 @@ k_knn_normals(const nksr_svh_t svh, const float* __restrict__ xyz, const float* 
   unsigned long long* key = buf[wid];
   const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
   const int L = svh.depth;
-  const unsigned long long kInf = 0xffffffffffffffffull;
   int got = 0;
   bool exact = false;
   for (int l = 0; l < L; ++l) {
@@ -184,40 +165,15 @@ k_knn_normals(const nksr_svh_t svh, const float* __restrict__ xyz, const float* 
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     if (total < 3 * k && l + 1 < L) continue;
     // ---- scan the block
-    for (int t = lane; t < kKnnBuf; t += 32) key[t] = kInf;
-    __syncwarp();
-    int fill = 0;                       // entries of the buffer in use (kept best first after a sort)
-    float bound = 3.0e38f;              // candidates at or beyond this squared distance cannot be among the k best
+    int fill;
+    float bound;
+    knn_reset(key, fill, bound, lane);
     for (int s = 0; s < 27; ++s) {
       const int sb = __shfl_sync(0xffffffffu, rb, s), se = __shfl_sync(0xffffffffu, re, s);
-      for (int q0 = sb; q0 < se; q0 += 32) {
-        const int q = q0 + lane;
-        float d2 = 3.0e38f;
-        if (q < se) {
-          const float dx = __ldg(xyz + 3 * (int64_t)q) - px, dy = __ldg(xyz + 3 * (int64_t)q + 1) - py,
-                      dz = __ldg(xyz + 3 * (int64_t)q + 2) - pz;
-          d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        }
-        const bool in = q < se && d2 < bound;
-        const unsigned bm = __ballot_sync(0xffffffffu, in);
-        if (fill + __popc(bm) > kKnnBuf) {       // no room: keep the k best, tighten the bound
-          knn_sort128(key, lane);
-          for (int t = k + lane; t < kKnnBuf; t += 32) key[t] = kInf;
-          fill = fill < k ? fill : k;
-          if (fill == k) bound = __uint_as_float((unsigned)(key[k - 1] >> 32));
-          __syncwarp();
-        }
-        const bool in2 = in && d2 < bound;
-        const unsigned bm2 = __ballot_sync(0xffffffffu, in2);
-        if (in2) key[fill + __popc(bm2 & ((1u << lane) - 1u))] =
-            ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)q;
-        fill += __popc(bm2);
-        __syncwarp();
-      }
+      knn_scan_range(key, fill, bound, k, xyz, sb, se, px, py, pz, lane);
     }
-    knn_sort128(key, lane);
-    got = fill < k ? fill : k;
-    const float dk2 = got > 0 ? __uint_as_float((unsigned)(key[got - 1] >> 32)) : 0.f;
+    float dk2;
+    got = knn_finish(key, fill, k, dk2, lane);
     const float hl = svh.voxel_size * (float)(1 << l);
     exact = got == k && dk2 <= hl * hl;
     if (exact || l + 1 == L) break;
