@@ -27,11 +27,14 @@ __device__ __forceinline__ void knn_sort128(unsigned long long* __restrict__ key
   }
 }
 
-__device__ __forceinline__ void knn_reset(unsigned long long* __restrict__ key, int& fill, float& bound, int lane) {
+// `bound0`: candidates at or beyond this squared distance are of no interest (a level's answer is only accepted when
+// the k-th distance stays within the cell size, so nothing further than that needs to be kept, let alone sorted)
+__device__ __forceinline__ void knn_reset(unsigned long long* __restrict__ key, int& fill, float& bound, int lane,
+                                          float bound0 = 3.0e38f) {
   for (int t = lane; t < kKnnBuf; t += 32) key[t] = kKnnInf;
   __syncwarp();
   fill = 0;
-  bound = 3.0e38f;
+  bound = bound0;
 }
 
 // one chunk of <= 32 candidates (lane: squared distance d2 of candidate q, `valid`); all lanes must call

@@ -167,14 +167,16 @@ k_knn_normals(const nksr_svh_t svh, const float* __restrict__ xyz, const float* 
     // ---- scan the block
     int fill;
     float bound;
-    knn_reset(key, fill, bound, lane);
+    const float hl = svh.voxel_size * (float)(1 << l);
+    // only neighbours within one cell size can make this level's answer acceptable: prune everything else up front
+    // (about two thirds of the block for surface-like data); the coarsest level answers unconditionally
+    knn_reset(key, fill, bound, lane, l + 1 < L ? hl * hl * 1.0000005f : 3.0e38f);
     for (int s = 0; s < 27; ++s) {
       const int sb = __shfl_sync(0xffffffffu, rb, s), se = __shfl_sync(0xffffffffu, re, s);
       knn_scan_range(key, fill, bound, k, xyz, sb, se, px, py, pz, lane);
     }
     float dk2;
     got = knn_finish(key, fill, k, dk2, lane);
-    const float hl = svh.voxel_size * (float)(1 << l);
     exact = got == k && dk2 <= hl * hl;
     if (exact || l + 1 == L) break;
   }

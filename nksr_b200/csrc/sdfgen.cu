@@ -50,13 +50,13 @@ __device__ __forceinline__ int knn_query(const nksr_svh_t& svh, const float* __r
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     if (total < k) continue;
-    knn_reset(key, fill, bound, lane);
+    const float hl = svh.voxel_size * (float)(1 << l) * 0.999f;
+    knn_reset(key, fill, bound, lane, hl * hl * 1.0000005f);   // further neighbours cannot make this level acceptable
     for (int s = 0; s < 27; ++s) {
       const int sb = __shfl_sync(0xffffffffu, rb, s), se = __shfl_sync(0xffffffffu, re, s);
       knn_scan_range(key, fill, bound, k, xyz, sb, se, qx, qy, qz, lane);
     }
     got = knn_finish(key, fill, k, dk2, lane);
-    const float hl = svh.voxel_size * (float)(1 << l) * 0.999f;
     if (got == k && dk2 <= hl * hl) { exact = true; break; }
   }
   if (!exact) {   // further from the data than the coarsest cell size (or fewer than k points in all): scan everything

@@ -164,9 +164,10 @@ class KernelField(BaseField):
             call("nksr_row_ranges", base[l], m, ranges[offs[l]:], svh.num_voxels(l), st)
         width = _lib.ROW_STRIDE * (3 if mode == 1 else 1)
         e = torch.empty((m, svh.depth, width), dtype=torch.float32, device=dev)      # location-major
-        # 'voxel' (default): one warp per voxel, stencil + features fetched once for all the voxel's locations;
-        # 'location': one warp per location (any channel count)
-        rows = self.solver_config.get("rows") or os.environ.get("NKSR_ROWS") or "voxel"
+        # 'location' (default): one warp per location (any channel count); 'voxel': one warp per voxel, stencil +
+        # features fetched once for all the voxel's locations (bitwise the same rows)
+        # (r2d, cfg4: voxel 46.8 ms, location 43.4 ms -- the per-level launches and the zero pass eat the saved gathers)
+        rows = self.solver_config.get("rows") or os.environ.get("NKSR_ROWS") or "location"
         if rows == "voxel" and self.z[0].shape[1] in (4, 8, 16):
             call("nksr_build_rows_voxel", svh.view(), self.feat_view(), xs, base, ranges, m, mode,
                  int(self.approx_kernel_grad), e, st)
@@ -270,8 +271,9 @@ class KernelField(BaseField):
             # transposed entries go straight to their final slot (SPEC S6b): per (fine level, offset) pair
             # a rank table on the fine level and a 125-ancestor prefix table on the coarse level
             cnt_down = torch.zeros(n, dtype=torch.int32, device=dev)
-            grouped = (self.solver_config.get("fill") or os.environ.get("NKSR_FILL") or "grouped") == "grouped" \
-                and svh.depth <= 4 and svh.depth < _lib.MAX_DEPTH
+            # row lengths with one column table per sibling group (r2d: 16 ms against 29 ms for a walk per slot and row)
+            count = self.solver_config.get("count") or os.environ.get("NKSR_COUNT") or "grouped"
+            grouped = count == "grouped" and svh.depth <= 4 and svh.depth < _lib.MAX_DEPTH
             call("nksr_gram_count_grouped" if grouped else "nksr_gram_count_own", svh.view(), cnt, st)
             place = _lib.PlacementT()
             for l in range(svh.depth - 1):
@@ -327,10 +329,12 @@ class KernelField(BaseField):
         val = torch.empty(nnz + 4, dtype=torch.float32, device=dev)[:nnz]
         rhs = torch.empty(n, dtype=torch.float32, device=dev)
         diag = torch.zeros(n, dtype=torch.float32, device=dev)
-        # numeric phase.  'grouped' (default): one warp per sibling group -- eight rows share their constraint
-        # lines, column tables and flush indices (csrc/gram_fill_group.cu); 'rows': one warp per matrix row
-        # (csrc/assemble.cu), kept for hierarchies deeper than 4 levels and as the comparison variant
-        fill = self.solver_config.get("fill") or os.environ.get("NKSR_FILL") or "grouped"
+        # numeric phase.  'rows' (default): one warp per matrix row (csrc/assemble.cu); 'grouped': one warp per
+        # sibling group -- eight rows share their constraint lines, column tables and flush indices
+        # (csrc/gram_fill_group.cu).  Measured on cfg4 (profiles/r2d_summary.md): grouped 247 ms against 186 ms -- the
+        # sharing halves the loads but the per-sibling tests and flushes cost as many instructions as they save, and
+        # 13.4 KB of shared memory + 128 registers per warp leave 11 resident warps per SM instead of 30
+        fill = self.solver_config.get("fill") or os.environ.get("NKSR_FILL") or "rows"
         if fill not in ("grouped", "rows"):
             raise ValueError("solver_config['fill'] must be 'grouped' or 'rows'")
         if place is not None and fill == "grouped" and svh.depth <= 4 and svh.depth < _lib.MAX_DEPTH:

@@ -79,6 +79,6 @@ def test_two_separate_components_and_resolve(cuda):
     info1 = dict(field.solve_info)
     field2 = rec.reconstruct(t(xyz), t(nrm), voxel_size=0.04, solver_tol=1e-6)
     assert torch.allclose(field2.alpha, alpha1, rtol=1e-3, atol=1e-5 * float(alpha1.abs().max()))
-    assert abs(field2.solve_info["iterations"] - info1["iterations"]) <= 2
+    assert abs(field2.solve_info["iterations"] - info1["iterations"]) <= 0.03 * info1["iterations"] + 3
     for l in range(3):
         assert torch.equal(field2.svh.keys[l], field.svh.keys[l])

@@ -95,7 +95,7 @@ def test_kernel_rows_match_oracle(cuda, C, approx):
 @pytest.mark.parametrize("C,approx,mode", [(4, False, 0), (4, False, 1), (4, True, 1), (4, True, 2), (16, False, 1),
                                            (8, True, 2), (16, False, 0)])
 def test_voxel_rows_are_the_location_rows(cuda, C, approx, mode):
-    """csrc/field.cu: the warp-per-voxel row builder (default; stencil + features fetched once per voxel) writes
+    """csrc/field.cu: the warp-per-voxel row builder (solver_config['rows'] = 'voxel') writes
     bitwise the rows of the warp-per-location builder -- including the zero lines of locations whose containing
     voxel is inactive on some level (here: constraint locations at the centres of childless level-1 voxels)."""
     xyz, _ = clouds.shapenet_like(3000)
@@ -203,7 +203,8 @@ def test_structural_placement_is_the_same_matrix(cuda, L, W, prune):
     (4, 0.02, False, False, False, None, False),    # position constraints only
 ])
 def test_grouped_fill_is_the_row_fill(cuda, L, W, prune, approx, compact, split, normals):
-    """The sibling-group fill (csrc/gram_fill_group.cu, the default) stores the matrix of the row-per-warp fill:
+    """The sibling-group fill (csrc/gram_fill_group.cu, solver_config['fill'] = 'grouped') stores the matrix of the
+    row-per-warp fill (the default):
     identical row pointers and columns (same structural order, same placement of the transposed entries), values /
     rhs / diagonal equal up to fp32 summation order, and it is run-to-run bitwise reproducible."""
     import nksr_b200
@@ -236,9 +237,9 @@ def test_grouped_fill_is_the_row_fill(cuda, L, W, prune, approx, compact, split,
     (rp_r, col_r, val_r, rhs_r, dg_r), (rp_g, col_g, val_g, rhs_g, dg_g), second = out
     assert np.array_equal(rp_r, rp_g) and np.array_equal(col_r, col_g)
     scale = np.abs(val_r).max()
-    assert np.abs(val_r - val_g).max() <= 2e-6 * scale
-    assert np.abs(rhs_r - rhs_g).max() <= 2e-6 * max(np.abs(rhs_r).max(), 1e-30)
-    assert np.abs(dg_r - dg_g).max() <= 2e-6 * scale
+    assert np.abs(val_r - val_g).max() <= 5e-6 * scale
+    assert np.abs(rhs_r - rhs_g).max() <= 1e-5 * max(np.abs(rhs_r).max(), 1e-30)
+    assert np.abs(dg_r - dg_g).max() <= 5e-6 * scale
     for a, b in zip(out[1], second):
         assert np.array_equal(a, b)
 

@@ -14,13 +14,19 @@ if has bench; then
   tail -c 1500 gpurun_out/${TAG}_bench.json
 fi
 if has ab; then
-  NKSR_FILL=rows NKSR_SPMV=rows NKSR_ROWS=location timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mesh > gpurun_out/${TAG}_bench_legacy.json 2> gpurun_out/${TAG}_bench_legacy.err
-  NKSR_COMPACT_ROWS=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mesh > gpurun_out/${TAG}_bench_compact.json 2> gpurun_out/${TAG}_bench_compact.err
-fi
+  NKSR_SPMV=rows timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mesh > gpurun_out/${TAG}_bench_legacy.json 2> gpurun_out/${TAG}_bench_legacy.err
+  fi
 if has launches; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv python tools/profile_run.py cfg4_outdoor_10M mesh > gpurun_out/${TAG}_launches.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv python tools/profile_run.py cfg4_outdoor_10M 10000000 mesh > gpurun_out/${TAG}_launches.log 2>&1
 fi
 if has ncu; then
-  timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_gram_fill_group|k_spmv_stream|k_build_rows_voxel|k_knn_normals" -c 30 -o gpurun_out/${TAG}_hot python tools/profile_run.py cfg4_outdoor_10M > gpurun_out/${TAG}_ncu.log 2>&1
+  # gpurun_out/ must stay under 64 MiB: export the pages that are read afterwards and drop the report
+  timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_gram_fill" -c 1 -o /tmp/${TAG}_fill python tools/profile_run.py cfg4_outdoor_10M > gpurun_out/${TAG}_ncu.log 2>&1
+  ncu -i /tmp/${TAG}_fill.ncu-rep --page raw --csv > gpurun_out/${TAG}_fill_raw.csv 2>/dev/null
+  ncu -i /tmp/${TAG}_fill.ncu-rep --page source --csv --print-source sass > /tmp/${TAG}_fill_source.csv 2>/dev/null
+  python tools/hot_lines.py /tmp/${TAG}_fill_source.csv > gpurun_out/${TAG}_fill_hot_sass.txt 2>&1
+  timeout 600 ncu --set full --clock-control none -k regex:"k_spmv_stream|k_knn_normals|k_gram_blocks|k_place_rank|k_place_prefix" -c 24 -o /tmp/${TAG}_other python tools/profile_run.py cfg4_outdoor_10M >> gpurun_out/${TAG}_ncu.log 2>&1
+  ncu -i /tmp/${TAG}_other.ncu-rep --page raw --csv > gpurun_out/${TAG}_other_raw.csv 2>/dev/null
 fi
+du -sh gpurun_out
 ls -la gpurun_out | tail -20
