@@ -256,6 +256,23 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
   float bsum = 0.f;
   const int sl = lane < 27 ? lane : 13;
   const int ldx = c_d27[sl][0], ldy = c_d27[sl][1], ldz = c_d27[sl][2];
+  // flush bases: lane us < 27 is also the source voxel u = i + d(us); base of u in the tile on every level without
+  // the lane's own stencil offset, packed two per word:  same level: (d+2) in the 5^3 box;  level l+k: position of
+  // (u >> k) in the 4^3 box that starts at ((i-1) >> k) - 1
+  const int lane_l0 = ldx * 25 + ldy * 5 + ldz, lane_lk = ldx * 16 + ldy * 4 + ldz;
+  unsigned flush_a, flush_b;
+  {
+    int b[4];
+    b[0] = 62 + lane_l0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const int ox = ((g.ux + ldx) >> k) - (((g.ux - 1) >> k) - 1), oy = ((g.uy + ldy) >> k) - (((g.uy - 1) >> k) - 1),
+                oz = ((g.uz + ldz) >> k) - (((g.uz - 1) >> k) - 1);
+      b[k] = 125 + 64 * (k - 1) + (ox << 4) + (oy << 2) + oz;
+    }
+    flush_a = (unsigned)b[0] | ((unsigned)b[1] << 16);
+    flush_b = (unsigned)b[2] | ((unsigned)b[3] << 16);
+  }
   // lane-parallel prefetch of the 27 neighbour voxels and their constraint-row ranges
   const int my_u = lane < 27 ? __ldg(svh.nbr27[l] + (int64_t)i * 27 + lane) : -1;
   int my_pb = 0, my_pe = 0, my_nb = 0, my_ne = 0;
@@ -361,18 +378,25 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
 #pragma unroll
     for (int k2 = 0; k2 < MAXL / 2; ++k2) { r[2 * k2] += r2[k2].x; r[2 * k2 + 1] += r2[k2].y; }
     }  // !use_blocks
-    // flush: every lane < 27 owns a distinct structural slot per level
-    if (lane < 27) {
-      const int udx = c_d27[us][0], udy = c_d27[us][1], udz = c_d27[us][2];
-      acc[(udx + ldx + 2) * 25 + (udy + ldy + 2) * 5 + (udz + ldz + 2)] += r[0];
-      const int vx = g.ux + udx, vy = g.uy + udy, vz = g.uz + udz;  // coords of u
+    // flush: every lane < 27 owns a distinct structural slot per level; slot = base of the source voxel (computed once
+    // per row by lane `us`, see flush_base above) + constant of the lane.  (r2b source page: the per-lane index
+    // arithmetic of the first version was 36 + 3 x 18 instructions 17 times per row, 21 % of the kernel.)
+    {
+      const unsigned wa = __shfl_sync(0xffffffffu, flush_a, us), wb = __shfl_sync(0xffffffffu, flush_b, us);
+      if (lane < 27) {
+        acc[(int)(wa & 0xffffu) + lane_l0] += r[0];
+        if (MAXL > 1 && 1 <= nup) acc[(int)(wa >> 16) + lane_lk] += r[1];
+        if (MAXL > 2 && 2 <= nup) acc[(int)(wb & 0xffffu) + lane_lk] += r[2];
+        if (MAXL > 3 && 3 <= nup) acc[(int)(wb >> 16) + lane_lk] += r[3];
 #pragma unroll
-      for (int k = 1; k < MAXL; ++k) {
-        if (k <= nup) {
-          const int ox = ((vx >> k) + ldx) - (((g.ux - 1) >> k) - 1);
-          const int oy = ((vy >> k) + ldy) - (((g.uy - 1) >> k) - 1);
-          const int oz = ((vz >> k) + ldz) - (((g.uz - 1) >> k) - 1);
-          acc[125 + 64 * (k - 1) + (ox << 4) + (oy << 2) + oz] += r[k];
+        for (int k = 4; k < MAXL; ++k) {      // hierarchies deeper than 4 levels: the general formula
+          if (k <= nup) {
+            const int vx = g.ux + c_d27[us][0], vy = g.uy + c_d27[us][1], vz = g.uz + c_d27[us][2];
+            const int ox = ((vx >> k) + ldx) - (((g.ux - 1) >> k) - 1);
+            const int oy = ((vy >> k) + ldy) - (((g.uy - 1) >> k) - 1);
+            const int oz = ((vz >> k) + ldz) - (((g.uz - 1) >> k) - 1);
+            acc[125 + 64 * (k - 1) + (ox << 4) + (oy << 2) + oz] += r[k];
+          }
         }
       }
     }
