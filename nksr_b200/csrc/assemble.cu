@@ -413,14 +413,13 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
     acc[(ldx + 2) * 25 + (ldy + 2) * 5 + (ldz + 2)] += cs.w_reg * bw * d;
   }
   __syncwarp();
-  // write-out in structural order
+  // write-out in structural order: the 125 same-level slots (4 chunks of 32), then the 64 slots of every coarser level
+  // (2 chunks each) -- the level offset k is uniform inside a chunk, so the box bounds, the ancestor and its parent are
+  // computed once per level instead of once per slot (r2b source page: 86 + 31 instructions per chunk of slot
+  // arithmetic in the first version, where a chunk could straddle two levels)
   const int64_t p0 = rowptr[row];
   int written = 0;
-  for (int t0 = 0; t0 < nslots; t0 += 32) {
-    const int t = t0 + lane;
-    int k = 0, ds = 0, sm = 0;
-    const int c = t >= nslots ? -1
-                              : (PLACED ? slot_column_place(svh, l, g, t, k, ds, sm) : slot_column(svh, l, g, t, k));
+  auto emit = [&](const int c, const int k, const int t, const int ds, const int sm) {
     const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
     if (c >= 0) {
       const int64_t p = p0 + written + __popc(m & ((1u << lane) - 1u));
@@ -437,6 +436,34 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
       }
     }
     written += __popc(m);
+  };
+  for (int t0 = 0; t0 < 125; t0 += 32) {
+    const int t = t0 + lane;
+    int k = 0;
+    const int c = t < 125 ? slot_column(svh, l, g, t, k) : -1;
+    emit(c, 0, t, 0, 0);
+  }
+#pragma unroll
+  for (int k = 1; k < MAXL; ++k) {
+    if (k <= nup) {
+      const int lox = ((g.ux - 1) >> k) - 1, loy = ((g.uy - 1) >> k) - 1, loz = ((g.uz - 1) >> k) - 1;
+      const int hix = ((g.ux + 1) >> k) + 1, hiy = ((g.uy + 1) >> k) + 1, hiz = ((g.uz + 1) >> k) + 1;
+      const int ax = g.ux >> k, ay = g.uy >> k, az = g.uz >> k;
+      const int a = g.anc[k];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int q = h * 32 + lane;
+        const int cx = lox + (q >> 4), cy = loy + ((q >> 2) & 3), cz = loz + (q & 3);
+        int c = -1, ds = 0, sm = 0;
+        if (a >= 0 && cx <= hix && cy <= hiy && cz <= hiz) {
+          c = lookup_near(svh, l + k, a, ax, ay, az, cx, cy, cz);
+          const int dx = cx - ax, dy = cy - ay, dz = cz - az;
+          ds = (dx + 2) * 25 + (dy + 2) * 5 + (dz + 2);
+          sm = ((dx == -2 || dx == 2) ? 4 : 0) | ((dy == -2 || dy == 2) ? 2 : 0) | ((dz == -2 || dz == 2) ? 1 : 0);
+        }
+        emit(c, k, 125 + 64 * (k - 1) + q, ds, sm);
+      }
+    }
   }
   if (lane == 0) rhs[row] = bsum;
 }
