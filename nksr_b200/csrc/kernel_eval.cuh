@@ -75,8 +75,7 @@ __device__ __forceinline__ LaneKernel eval_level_lane(const int32_t* __restrict_
   }
   float dot = 0.f, ddot[3] = {0.f, 0.f, 0.f};
   const float* zr = z + (int64_t)(ok ? r.nb : 0) * C;
-  for (int c = 0; c < C; ++c) {
-    float zc = ok ? __ldg(zr + c) : 0.f;
+  auto channel = [&](const float zc) {
     float phi = warp_sum(T3 * zc);
     dot = fmaf(phi, zc, dot);
     if (GRAD && fullgrad) {
@@ -86,6 +85,16 @@ __device__ __forceinline__ LaneKernel eval_level_lane(const int32_t* __restrict_
         ddot[a] = fmaf(dphi, zc, ddot[a]);
       }
     }
+  };
+  if ((C & 3) == 0) {
+    // the 27 lanes read 27 different feature rows: every load instruction is a 27-wavefront gather in L1, so fetch
+    // four channels per instruction (rows of C = 4, 8, 16 ... floats are 16-byte aligned); same arithmetic, same order
+    for (int c4 = 0; c4 < C; c4 += 4) {
+      const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(zr + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      channel(v.x); channel(v.y); channel(v.z); channel(v.w);
+    }
+  } else {
+    for (int c = 0; c < C; ++c) channel(ok ? __ldg(zr + c) : 0.f);
   }
   r.k = ok ? B3 * dot : 0.f;
   r.dot = ok ? dot : 0.f;

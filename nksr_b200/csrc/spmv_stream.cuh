@@ -20,7 +20,7 @@ namespace {
 constexpr int kTile = 4096;             // entries per tile: 16 KB of columns + 16 KB of values
 constexpr int kTileRows = 512;          // row pointers staged per tile (int64): 4 KB
 constexpr int kStages = 3;
-constexpr int kStreamWarps = 8;         // consumer warps per CTA
+constexpr int kStreamWarps = 16;        // consumer warps per CTA (r2e: 8 warps left the x gathers latency bound)
 constexpr int kStreamThreads = (kStreamWarps + 1) * 32;   // + the producer warp
 constexpr int kStreamCtasPerSm = 2;
 

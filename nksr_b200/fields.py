@@ -119,6 +119,8 @@ class KernelField(BaseField):
                 with torch.no_grad():
                     f = mod(f)
             f = f.contiguous()
+            if f.data_ptr() % 16:                     # the kernels fetch four channels per 128-bit load
+                f = f.clone()
             C_ = f.shape[1] if C_ is None else C_
             if f.shape[1] != C_:
                 raise ValueError("all levels must share one kernel_dim")
