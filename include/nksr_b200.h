@@ -204,13 +204,18 @@ NKSR_API int nksr_pcg_solve(const int64_t* rowptr, const int32_t* col, const flo
  * result up to the summation order inside a row (fixed, reproducible).  Bulk copies move whole 16-byte units: rowptr
  * must be readable up to index n + 1 (n + 2 entries) and col / val up to the next multiple of 4 entries. */
 NKSR_API size_t nksr_pcg_stream_workspace_bytes(int64_t n, int64_t nnz);
+/* rows [0, split_row) -- entries [0, split_nnz), split_nnz = rowptr[split_row] -- are streamed; rows >= split_row (the
+ * coarse levels, whose transposed segments make rows of tens of thousands of entries) go through the warp-per-row
+ * kernel, where a long row streams well and does not stall a tile behind one warp.  split_row = n streams everything. */
 NKSR_API int nksr_pcg_solve_stream(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag,
-                          const float* b, float* x, int64_t n, int64_t nnz, float tol, int max_iter, int check_every,
-                          int profile, void* ws, size_t ws_bytes, double* info, void* stream);
+                          const float* b, float* x, int64_t n, int64_t nnz, int64_t split_row, int64_t split_nnz,
+                          float tol, int max_iter, int check_every, int profile, void* ws, size_t ws_bytes,
+                          double* info, void* stream);
 /* y = A x through the same tile stream (plan_buf: nksr_spmv_plan_bytes(nnz) bytes of scratch) */
 NKSR_API size_t nksr_spmv_plan_bytes(int64_t nnz);
 NKSR_API int nksr_spmv_stream(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
-                     int64_t n, int64_t nnz, void* plan_buf, size_t plan_bytes, void* stream);
+                     int64_t n, int64_t nnz, int64_t split_row, int64_t split_nnz, void* plan_buf,
+                     size_t plan_bytes, void* stream);
 
 /* ---- e: step kernels of the multi-GPU solve (one global system, SURVEY section 8e mapping B).  A
  * Chronopoulos-Gear arrangement of the same Jacobi-PCG: per iteration ONE halo exchange of u = M^-1 r, one

@@ -84,9 +84,9 @@ _SIGNATURES = {
     "nksr_pcg_workspace_bytes": ("z", "q"),
     "nksr_pcg_solve": ("i", "pppppp" + "qfiii" + "pzdp"),
     "nksr_pcg_stream_workspace_bytes": ("z", "qq"),
-    "nksr_pcg_solve_stream": ("i", "pppppp" + "qqfiii" + "pzdp"),
+    "nksr_pcg_solve_stream": ("i", "pppppp" + "qqqqfiii" + "pzdp"),
     "nksr_spmv_plan_bytes": ("z", "q"),
-    "nksr_spmv_stream": ("i", "ppppp" + "qq" + "pzp"),
+    "nksr_spmv_stream": ("i", "ppppp" + "qqqq" + "pzp"),
     "nksr_dcg_workspace_bytes": ("z", ""),
     "nksr_dcg_init": ("i", "pppppppp" + "q" + "pz" + "pp"),
     "nksr_dcg_begin": ("i", "ppfip"),

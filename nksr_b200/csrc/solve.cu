@@ -241,8 +241,11 @@ static void launch_iteration(const int64_t* rowptr, const int32_t* col, const fl
   double* rz_cur = parity ? w.rz1 : w.rz0;
   double* rz_new = parity ? w.rz0 : w.rz1;
   if (e0) cudaEventRecord(e0, s);
-  if (plan) {   // tile stream through the TMA engine + boundary rows + p.Ap
-    spmv_stream_launch(rowptr, col, val, w.p, w.ap, n, *plan, &w.ctrl->done, s);
+  if (plan) {   // tile stream through the TMA engine + boundary rows, long coarse rows warp per row, then p.Ap
+    spmv_stream_launch(rowptr, col, val, w.p, w.ap, *plan, &w.ctrl->done, s);
+    if (plan->n_rows < n)
+      k_spmv<false><<<kGrid, kBlock, 0, s>>>(rowptr + plan->n_rows, col, val, w.p, w.ap + plan->n_rows,
+                                             n - plan->n_rows, nullptr, w.ctrl);
     k_dot_partials<<<kGrid, 256, 0, s>>>(w.p, w.ap, n, w.pap, &w.ctrl->done);
   } else {
     k_spmv<true><<<kGrid, kBlock, 0, s>>>(rowptr, col, val, w.p, w.ap, n, w.pap, w.ctrl);
@@ -382,14 +385,18 @@ size_t nksr_pcg_stream_workspace_bytes(int64_t n, int64_t nnz) {
 }
 
 int nksr_pcg_solve_stream(const int64_t* rowptr, const int32_t* col, const float* val, const float* diag,
-                          const float* b, float* x, int64_t n, int64_t nnz, float tol, int max_iter, int check_every,
-                          int profile, void* ws, size_t ws_bytes, double* info, void* stream) {
-  if (n <= 0 || nnz <= 0) return NKSR_E_INVALID;
+                          const float* b, float* x, int64_t n, int64_t nnz, int64_t split_row, int64_t split_nnz,
+                          float tol, int max_iter, int check_every, int profile, void* ws, size_t ws_bytes,
+                          double* info, void* stream) {
+  if (n <= 0 || nnz <= 0 || split_row < 0 || split_row > n || split_nnz < 0 || split_nnz > nnz) return NKSR_E_INVALID;
   if (ws_bytes < nksr_pcg_stream_workspace_bytes(n, nnz)) return NKSR_E_WORKSPACE;
   const size_t base = nksr_pcg_workspace_bytes(n);
-  SpmvPlan plan = spmv_plan_carve(reinterpret_cast<unsigned char*>(ws) + base, nnz);
+  if (split_row == 0 || split_nnz == 0)     // nothing to stream: the plain solver
+    return pcg_solve_impl(rowptr, col, val, diag, b, x, n, tol, max_iter, check_every, profile, ws, base, info, stream,
+                          nullptr);
+  SpmvPlan plan = spmv_plan_carve(reinterpret_cast<unsigned char*>(ws) + base, split_row, split_nnz);
   if (spmv_stream_prepare() != NKSR_OK || spmv_stream_sm_count() <= 0) return NKSR_E_CUDA;
-  if (spmv_plan_build(rowptr, n, plan, as_stream(stream)) != NKSR_OK) return NKSR_E_CUDA;
+  if (spmv_plan_build(rowptr, plan, as_stream(stream)) != NKSR_OK) return NKSR_E_CUDA;
   return pcg_solve_impl(rowptr, col, val, diag, b, x, n, tol, max_iter, check_every, profile, ws, base, info, stream,
                         &plan);
 }
@@ -397,15 +404,28 @@ int nksr_pcg_solve_stream(const int64_t* rowptr, const int32_t* col, const float
 size_t nksr_spmv_plan_bytes(int64_t nnz) { return spmv_plan_bytes(nnz > 0 ? nnz : 1); }
 
 int nksr_spmv_stream(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, float* y, int64_t n,
-                     int64_t nnz, void* plan_buf, size_t plan_bytes, void* stream) {
-  if (n <= 0 || nnz <= 0 || !plan_buf) return NKSR_E_INVALID;
+                     int64_t nnz, int64_t split_row, int64_t split_nnz, void* plan_buf, size_t plan_bytes,
+                     void* stream) {
+  if (n <= 0 || nnz <= 0 || !plan_buf || split_row < 0 || split_row > n || split_nnz < 0 || split_nnz > nnz)
+    return NKSR_E_INVALID;
   if (plan_bytes < spmv_plan_bytes(nnz)) return NKSR_E_WORKSPACE;
   cudaStream_t s = as_stream(stream);
-  SpmvPlan plan = spmv_plan_carve(plan_buf, nnz);
-  if (spmv_stream_prepare() != NKSR_OK) return NKSR_E_CUDA;
-  if (spmv_plan_build(rowptr, n, plan, s) != NKSR_OK) return NKSR_E_CUDA;
   if (cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), s) != cudaSuccess) return NKSR_E_CUDA;   // empty rows
-  return spmv_stream_launch(rowptr, col, val, x, y, n, plan, nullptr, s);
+  if (split_row > 0 && split_nnz > 0) {
+    SpmvPlan plan = spmv_plan_carve(plan_buf, split_row, split_nnz);
+    if (spmv_stream_prepare() != NKSR_OK) return NKSR_E_CUDA;
+    if (spmv_plan_build(rowptr, plan, s) != NKSR_OK) return NKSR_E_CUDA;
+    const int rc = spmv_stream_launch(rowptr, col, val, x, y, plan, nullptr, s);
+    if (rc != NKSR_OK) return rc;
+  }
+  if (split_row < n) {
+    int grid = (int)((n - split_row + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    if (grid > kGrid) grid = kGrid;
+    k_spmv<false><<<grid, kBlock, 0, s>>>(rowptr + split_row, col, val, x, y + split_row, n - split_row, nullptr,
+                                          nullptr);
+    NKSR_CHECK_LAUNCH();
+  }
+  return NKSR_OK;
 }
 
 }  // extern "C"

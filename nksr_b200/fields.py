@@ -195,8 +195,13 @@ class KernelField(BaseField):
         if spmv == "stream":
             nb = call("nksr_pcg_stream_workspace_bytes", n, sysm.nnz)
             ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            # rows of the two finest levels are streamed; the coarse rows (transposed segments of up to tens of
+            # thousands of entries) go warp per row, where a long row streams well and cannot hold a tile up
+            offs = self.svh.offsets
+            split_row = offs[2] if self.svh.depth > 2 else n
+            split_nnz = int(sysm.rowptr[split_row].item()) if split_row < n else sysm.nnz
             call("nksr_pcg_solve_stream", sysm.rowptr, sysm.col, sysm.val, sysm.diag, sysm.rhs, alpha, n, sysm.nnz,
-                 float(self.solver_config["tol"]), int(self.solver_config["max_iter"]),
+                 split_row, split_nnz, float(self.solver_config["tol"]), int(self.solver_config["max_iter"]),
                  int(self.solver_config["check_every"]), profile, ws, nb, info, stream_ptr(dev))
         else:
             nb = call("nksr_pcg_workspace_bytes", n)

@@ -30,3 +30,7 @@ if has ncu; then
 fi
 du -sh gpurun_out
 ls -la gpurun_out | tail -20
+if has spmvncu; then
+  timeout 600 ncu --set full --clock-control none -k regex:"k_spmv_stream|k_spmv" -c 6 -o /tmp/${TAG}_spmv python tools/profile_run.py cfg4_outdoor_10M > gpurun_out/${TAG}_spmv_ncu.log 2>&1
+  ncu -i /tmp/${TAG}_spmv.ncu-rep --page raw --csv > gpurun_out/${TAG}_spmv_raw.csv 2>/dev/null
+fi
