@@ -378,18 +378,18 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
         const float* p0 = cs.e_nrm + ((int64_t)q * L + l) * (3 * NKSR_ROW_STRIDE);
         const float* t = cs.t_nrm + (int64_t)q * 3;
 #pragma unroll
+        // (the own coefficient stays a broadcast LOAD here: fetching it by shuffle from the level-l line -- as the position
+        // loop does -- ties the three axes' loads to the shuffles' completion and cost 42 ms on cfg4, r2g)
         for (int ax = 0; ax < 3; ++ax) {
-          const float* pk = p0 + ax * NKSR_ROW_STRIDE + lane;
-          float ln[MAXL];
-#pragma unroll
-          for (int k = 0; k < MAXL; ++k) ln[k] = k <= nup ? __ldg(pk + k * nrm_level) : 0.f;
-          // the row voxel's own coefficient is slot si of the level-l line that is already here: a shuffle, not a
-          // fourth kind of load (r2b source page: 18 loads per visit of this loop, 52 % of the kernel's stall samples)
-          const float a = cs.w_nrm * __shfl_sync(0xffffffffu, ln[0], si);
+          const float a = cs.w_nrm * __ldg(p0 + ax * NKSR_ROW_STRIDE + si);
           bsum = fmaf(a, __ldg(t + ax), bsum);
+          const float* pk = p0 + ax * NKSR_ROW_STRIDE + lane;
 #pragma unroll
-          for (int k2 = 0; k2 < MAXL / 2; ++k2)
-            r2[k2] = __ffma2_rn(make_float2(a, a), make_float2(ln[2 * k2], ln[2 * k2 + 1]), r2[k2]);
+          for (int k2 = 0; k2 < MAXL / 2; ++k2) {
+            const float l0 = 2 * k2 <= nup ? __ldg(pk + (2 * k2) * nrm_level) : 0.f;
+            const float l1 = 2 * k2 + 1 <= nup ? __ldg(pk + (2 * k2 + 1) * nrm_level) : 0.f;
+            r2[k2] = __ffma2_rn(make_float2(a, a), make_float2(l0, l1), r2[k2]);
+          }
         }
       }
     }

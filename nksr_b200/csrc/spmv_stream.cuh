@@ -5,8 +5,11 @@
 // tiles (column indices, values and the slice of row pointers that covers them) from HBM into a ring of
 // shared-memory stages with 1-D bulk async copies (cp.async.bulk.shared::cluster.global, the TMA engine; SASS
 // UBLKCP) that signal an mbarrier with their byte count; the consumer warps never issue a load for the matrix:
-//   one warp per row of the tile multiplies and sums the row straight from shared memory (the x gathers are the only
-//   global loads of the kernel) in a fixed order and writes y.
+//   phase 1  every thread turns its share of the tile into products  val * x[col]  in place (the x gathers are
+//            the only global loads of the kernel, perfectly balanced, 8 independent gathers per thread);
+//   phase 2  one warp per row sums the row's products from shared memory in a fixed order and writes y.
+// (A one-phase consumer -- warp per row straight from shared memory, no CTA barrier, 24 warps -- was measured slower:
+// 3.1 TB/s on the short rows against 4.5 TB/s, r2g.)
 // A row cut by a tile boundary is owned by the tile it starts in; the tiles it continues into leave their part in
 // head[tile] and k_spmv_heads adds the parts in tile order -- no atomics, bitwise reproducible.
 // The memory pipeline (kStages x 36 KB per CTA, 2 CTAs per SM) is independent of what the warps are waiting for,
@@ -19,7 +22,7 @@ namespace {
 constexpr int kTile = 4096;             // entries per tile: 16 KB of columns + 16 KB of values
 constexpr int kTileRows = 512;          // row pointers staged per tile (int64): 4 KB
 constexpr int kStages = 3;
-constexpr int kStreamWarps = 24;        // consumer warps per CTA (2 CTAs per SM: 48 gathering warps + 2 producers)
+constexpr int kStreamWarps = 16;        // consumer warps per CTA (r2e: 8 warps left the x gathers latency bound)
 constexpr int kStreamThreads = (kStreamWarps + 1) * 32;   // + the producer warp
 constexpr int kStreamCtasPerSm = 2;
 
@@ -132,11 +135,28 @@ k_spmv_stream(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ co
     mbar_wait(&sm.full[s], use & 1);
     const int64_t e0 = t * kTile;
     const int cnt = (int)((nnz - e0 < kTile) ? (nnz - e0) : kTile);
-    // one warp per row of the tile: columns and values come from shared memory, the x gathers are the only global
-    // loads (four independent 32-entry groups in flight per warp).  No CTA-wide phase: a warp that is done with its
-    // rows releases the stage and moves on to the next tile, so the row-length imbalance inside a tile averages out
-    // over the ring.  (First versions: products in place + a second reduction phase behind a named barrier -- 41
-    // instructions per 32 entries, issue bound at 7.9 ms, r2f; and before that a serialised product loop, 17.7 ms, r2d.)
+    // phase 1: products in place.  All 16 column indices of the thread first, then 16 independent x gathers in flight,
+    // then the multiplies (a loop of  val[e] *= x[col[e]]  serialises on the shared-memory store: measured 17.7 ms per
+    // SpMV, 8 stalled warps per issue, r2d)
+    {
+      constexpr int kPer = kTile / (kStreamWarps * 32);
+      int c[kPer];
+      float xv[kPer];
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int e = tid + j * (kStreamWarps * 32);
+        c[j] = e < cnt ? st.col[e] : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) xv[j] = __ldg(x + c[j]);
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int e = tid + j * (kStreamWarps * 32);
+        st.val[e] *= xv[j];
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kStreamWarps * 32) : "memory");
+    // phase 2: one warp per row of the tile
     const int r0 = first_row[t];
     const int64_t ra = r0 & ~1;
     int64_t rcount = (int64_t)first_row[t + 1] + 2 - ra;
@@ -150,21 +170,16 @@ k_spmv_stream(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ co
       if (b >= e1) break;
       const int64_t e = rp[row - ra + 1];
       const int lo = (int)((b > e0 ? b : e0) - e0), hi = (int)((e < e1 ? e : e1) - e0);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      for (int p = lo + lane; p < hi; p += 128) {
-        const bool q1 = p + 32 < hi, q2 = p + 64 < hi, q3 = p + 96 < hi;
-        const int c0 = st.col[p], c1 = q1 ? st.col[p + 32] : 0, c2 = q2 ? st.col[p + 64] : 0, c3 = q3 ? st.col[p + 96] : 0;
-        const float x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-        s0 = fmaf(st.val[p], x0, s0);
-        s1 = fmaf(q1 ? st.val[p + 32] : 0.f, x1, s1);
-        s2 = fmaf(q2 ? st.val[p + 64] : 0.f, x2, s2);
-        s3 = fmaf(q3 ? st.val[p + 96] : 0.f, x3, s3);
-      }
-      const float acc = warp_sum((s0 + s1) + (s2 + s3));
+      float acc = 0.f;
+      for (int p = lo + lane; p < hi; p += 32) acc += st.val[p];
+      acc = warp_sum(acc);
       if (lane == 0) {
         if (b >= e0) y[row] = acc; else head[t] = acc;
       }
     }
+    // the stage was written through the generic proxy (products in place); order those writes before the bulk
+    // copy (async proxy) that refills it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);
   }

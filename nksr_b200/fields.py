@@ -187,9 +187,10 @@ class KernelField(BaseField):
         alpha = torch.empty(n, dtype=torch.float32, device=dev)
         info = (C.c_double * 8)()
         profile = int(bool(self.solver_config.get("profile")))
-        # 'stream' (default): the CSR arrays reach the SMs as tiles moved by bulk async copies (TMA engine) into a
-        # shared-memory ring (csrc/spmv_stream.cuh); 'rows': one warp per row with register loads (csrc/solve.cu)
-        spmv = self.solver_config.get("spmv") or os.environ.get("NKSR_SPMV") or "stream"
+        # 'rows' (default): one warp per row with register loads (csrc/solve.cu); 'stream': the CSR arrays reach the SMs
+        # as tiles moved by bulk async copies (TMA engine) into a shared-memory ring (csrc/spmv_stream.cuh)
+        # measured on cfg4 (profiles/r2g_summary.md): rows 7.45 ms per SpMV (0.717 of the copy peak), stream 7.96 ms
+        spmv = self.solver_config.get("spmv") or os.environ.get("NKSR_SPMV") or "rows"
         if spmv not in ("stream", "rows"):
             raise ValueError("solver_config['spmv'] must be 'stream' or 'rows'")
         if spmv == "stream":

@@ -14,7 +14,7 @@ if has bench; then
   tail -c 1500 gpurun_out/${TAG}_bench.json
 fi
 if has ab; then
-  NKSR_SPMV=rows timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mesh > gpurun_out/${TAG}_bench_legacy.json 2> gpurun_out/${TAG}_bench_legacy.err
+  NKSR_SPMV=stream timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mesh > gpurun_out/${TAG}_bench_stream.json 2> gpurun_out/${TAG}_bench_stream.err
   fi
 if has launches; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv python tools/profile_run.py cfg4_outdoor_10M 10000000 mesh > gpurun_out/${TAG}_launches.log 2>&1
