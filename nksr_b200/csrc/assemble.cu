@@ -21,6 +21,8 @@
 // 27 x 27 products are reduced once per voxel by k_gram_blocks and the rows only gather block lines.
 // Optional compact gradient rows (approx_kernel_grad: one line <phi,z_s> + tau per location and level,
 // the three rows rebuilt with nine FMAs) trade 2/3 of the row memory for ALU work.
+#include <stdlib.h>
+
 #include <cub/cub.cuh>
 
 #include "gram_common.cuh"
@@ -374,12 +376,15 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
         }
       }
     } else {
+      // MINB == 3 ("wide" variant, NKSR_FILL_VARIANT=wide): 85 registers, two normal locations = 30 line loads in
+      // flight per warp instead of 15, three blocks per SM instead of four
+#pragma unroll(MINB == 3 ? 2 : 1)
       for (int q = nb; q < ne; ++q) {
         const float* p0 = cs.e_nrm + ((int64_t)q * L + l) * (3 * NKSR_ROW_STRIDE);
         const float* t = cs.t_nrm + (int64_t)q * 3;
-#pragma unroll
         // (the own coefficient stays a broadcast LOAD here: fetching it by shuffle from the level-l line -- as the position
         // loop does -- ties the three axes' loads to the shuffles' completion and cost 42 ms on cfg4, r2g)
+#pragma unroll
         for (int ax = 0; ax < 3; ++ax) {
           const float a = cs.w_nrm * __ldg(p0 + ax * NKSR_ROW_STRIDE + si);
           bsum = fmaf(a, __ldg(t + ax), bsum);
@@ -703,8 +708,11 @@ int launch_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_const
                                                                            rhs, diag, cursor, place)
   // 4 resident blocks per SM (64 registers) for depth <= 4; 5 blocks (48 registers) was measured
   // 1.7x slower (register starvation cuts the loads in flight per warp)
+  static const bool wide = [] { const char* v = getenv("NKSR_FILL_VARIANT"); return v && v[0] == 'w'; }();
   if (svh->depth <= 4) {
-    if (c->nrm_compact) NKSR_FILL(true, 4, 4); else NKSR_FILL(false, 4, 4);
+    if (c->nrm_compact) NKSR_FILL(true, 4, 4);
+    else if (wide) NKSR_FILL(false, 4, 3);
+    else NKSR_FILL(false, 4, 4);
   } else {
     if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH, 2); else NKSR_FILL(false, NKSR_MAX_DEPTH, 2);
   }

@@ -210,6 +210,107 @@ k_evaluate(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ alpha, co
   }
 }
 
+// f(x) for RUNS of consecutive queries (C == 4, value only): the mesher evaluates lattice points in Morton order, so
+// consecutive queries share their containing voxel on the coarse levels almost always and on the finest level about
+// half of the time.  One warp walks kEvalRun consecutive queries and keeps, per level, the containing voxel with its
+// 27 neighbours, their features (one float4) and coefficients in registers; a level is re-fetched only when the
+// query leaves the voxel.  k_evaluate re-gathers all of it per query and level (three 27-wavefront gathers each; r2e:
+// 114 ms for the two evaluations of one cfg4 extraction).  Same arithmetic in the same order: bitwise the values of
+// k_evaluate<false>.
+constexpr int kEvalRun = 8;
+constexpr int kEvalMaxL = 4;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_evaluate_runs(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ alpha, const float* __restrict__ xyz,
+                int64_t m, float* __restrict__ f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q0 = (blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5)) * kEvalRun;
+  if (q0 >= m) return;
+  const int L = svh.depth;
+  const float half_w = svh.voxel_size * 0.5f;
+  const double inv0 = 1.0 / (double)svh.voxel_size;
+  int dx, dy, dz;
+  slot_to_d(lane < 27 ? lane : 13, dx, dy, dz);
+  // cached state per level: voxel coordinates, index, this lane's neighbour, its features and coefficient
+  int cux[kEvalMaxL], cuy[kEvalMaxL], cuz[kEvalMaxL], cidx[kEvalMaxL], cnb[kEvalMaxL];
+  float4 cz[kEvalMaxL];
+  float ca[kEvalMaxL];
+#pragma unroll
+  for (int ll = 0; ll < kEvalMaxL; ++ll) {      // indexed by position in the coarse-to-fine walk: static after unrolling
+    cux[ll] = cuy[ll] = cuz[ll] = -1; cidx[ll] = -1; cnb[ll] = -1; ca[ll] = 0.f;
+    cz[ll] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int64_t q1 = q0 + kEvalRun < m ? q0 + kEvalRun : m;
+  for (int64_t i = q0; i < q1; ++i) {
+    const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
+    int u[3];
+    bool bad = false;
+    {
+      const float p[3] = {px, py, pz};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float q = floorf(__fdiv_rn(p[a], half_w));
+        if (!(q > -(float)(NKSR_HALF_OFFSET - 16) && q < (float)(NKSR_HALF_OFFSET - 16))) { bad = true; q = 0.f; }
+        u[a] = (int)q + NKSR_HALF_OFFSET;
+      }
+    }
+    float accf = 0.f;
+    int idx = -1;
+    bool alive = !bad && svh.n[L - 1] > 0;
+#pragma unroll
+    for (int ll = 0; ll < kEvalMaxL; ++ll) {
+      const int l = L - 1 - ll;                    // coarse to fine
+      if (l < 0 || !alive) continue;
+      const int vx = u[0] >> (l + 1), vy = u[1] >> (l + 1), vz = u[2] >> (l + 1);
+      if (vx != cux[ll] || vy != cuy[ll] || vz != cuz[ll]) {   // left the voxel on this level: re-fetch it
+        int nidx;
+        if (l == L - 1) {
+          nidx = find_key(svh.keys[l], svh.n[l], morton3(vx, vy, vz));
+        } else {
+          const int slot = (((u[0] >> (l + 1)) & 1) << 2) | (((u[1] >> (l + 1)) & 1) << 1) | ((u[2] >> (l + 1)) & 1);
+          nidx = idx >= 0 ? __ldg(svh.child8[l + 1] + (int64_t)idx * 8 + slot) : -1;
+        }
+        cux[ll] = vx; cuy[ll] = vy; cuz[ll] = vz; cidx[ll] = nidx;
+        cnb[ll] = -1; ca[ll] = 0.f; cz[ll] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nidx >= 0 && lane < 27) {
+          const int nb = __ldg(svh.nbr27[l] + (int64_t)nidx * 27 + lane);
+          cnb[ll] = nb;
+          if (nb >= 0) {
+            cz[ll] = __ldg(reinterpret_cast<const float4*>(feat.z[l] + (int64_t)nb * 4));
+            ca[ll] = __ldg(alpha + svh.offset[l] + nb);
+          }
+        }
+      }
+      idx = cidx[ll];
+      if (idx < 0) { alive = false; continue; }   // parent closure: nothing active below
+      // ---- K_l(x, nb) exactly as eval_level_lane<false> computes it
+      const int off = level_offset(l);
+      const double inv = inv0 * (1.0 / (double)(1 << l));
+      const float tx = (float)((double)px * inv - ((double)(vx - off) + 0.5));
+      const float ty = (float)((double)py * inv - ((double)(vy - off) + 0.5));
+      const float tz = (float)((double)pz * inv - ((double)(vz - off) + 0.5));
+      float bx, dbx, ttx, dtx, by, dby, tty, dty, bz, dbz, ttz, dtz;
+      axis_weights(tx, dx, bx, dbx, ttx, dtx);
+      axis_weights(ty, dy, by, dby, tty, dty);
+      axis_weights(tz, dz, bz, dbz, ttz, dtz);
+      const bool ok = cnb[ll] >= 0;
+      const float B3 = bx * by * bz;
+      const float T3 = ok ? ttx * tty * ttz : 0.f;
+      float dot = 0.f;
+      const float zc[4] = {cz[ll].x, cz[ll].y, cz[ll].z, cz[ll].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float phi = warp_sum(T3 * zc[c]);
+        dot = fmaf(phi, zc[c], dot);
+      }
+      const float kval = ok ? B3 * dot : 0.f;
+      accf = fmaf(ok ? ca[ll] : 0.f, kval, accf);
+    }
+    accf = warp_sum(accf);
+    if (lane == 0) f[i] = accf;
+  }
+}
+
 // LayerField mask: 1 when the containing voxel of some level < adaptive_depth is active
 __global__ void k_layer_mask(nksr_svh_t svh, const float* __restrict__ xyz, int64_t m, int adaptive_depth,
                              float* __restrict__ out) {
@@ -298,6 +399,9 @@ int nksr_evaluate(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* a
   if (want_grad)
     k_evaluate<true><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, alpha, xyz, m,
                                                                           !approx_kernel_grad, f, grad);
+  else if (feat->channels == 4 && svh->depth <= kEvalMaxL)
+    k_evaluate_runs<<<grid_for((m + kEvalRun - 1) / kEvalRun, kWarpsPerBlock), kWarpsPerBlock * 32, 0,
+                      as_stream(stream)>>>(*svh, *feat, alpha, xyz, m, f);
   else
     k_evaluate<false><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(*svh, *feat, alpha, xyz, m, false, f,
                                                                            grad);

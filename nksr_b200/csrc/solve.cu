@@ -50,13 +50,10 @@ k_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
   const int wid = threadIdx.x >> 5;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   double local = 0.0;
-  int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + wid;
-  // the row pointers of the NEXT row of this warp are fetched while the current row streams: one dependent round
-  // trip less per row (rows of the two finest levels are ~200 entries, i.e. two iterations of the loop below)
-  int64_t b_next = row < n ? __ldg(rowptr + row) : 0, e_next = row < n ? __ldg(rowptr + row + 1) : 0;
-  for (; row < n; row += nwarps) {
-    const int64_t b = b_next, e = e_next;
-    if (row + nwarps < n) { b_next = __ldg(rowptr + row + nwarps); e_next = __ldg(rowptr + row + nwarps + 1); }
+  for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + wid; row < n; row += nwarps) {
+    const int64_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    // (prefetching the next row's pointers was tried: 10.4 ms instead of 7.45 ms, r2h -- the two loop-carried 64-bit
+    // values push the kernel past the 32 registers that keep the persistent 148 x 8 grid resident)
     // matrix stream: evict-first loads (read once per SpMV); x: read-only path, stays in L1/L2.
     // Four independent 128 B column + value requests per lane keep ~1 KB per warp in flight.
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
