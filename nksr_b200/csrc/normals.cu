@@ -170,13 +170,23 @@ k_knn_normals(const nksr_svh_t svh, const float* __restrict__ xyz, const float* 
     const float hl = svh.voxel_size * (float)(1 << l);
     // only neighbours within one cell size can make this level's answer acceptable: prune everything else up front
     // (about two thirds of the block for surface-like data); the coarsest level answers unconditionally
-    knn_reset(key, fill, bound, lane, l + 1 < L ? hl * hl * 1.0000005f : 3.0e38f);
-    for (int s = 0; s < 27; ++s) {
-      const int sb = __shfl_sync(0xffffffffu, rb, s), se = __shfl_sync(0xffffffffu, re, s);
-      knn_scan_range(key, fill, bound, k, xyz, sb, se, px, py, pz, lane);
+    const float full = l + 1 < L ? hl * hl * 1.0000005f : 3.0e38f;
+    // first try a tighter radius: for surface-like data the block's `total` points cover ~9 h^2, so ~1.7 k of them lie
+    // within r^2 = 9 h^2 * 1.7 k / (pi * total); then the candidate buffer rarely overflows (one sort per point instead
+    // of two or three -- the bitonic network is this kernel's cost, r2f).  Too tight (fewer than k found): scan again.
+    float first = 9.0f * hl * hl * (1.7f * (float)k) / (3.14159265f * (float)total);
+    first = first < full ? first : full;
+    float dk2 = 0.f;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      const float b0 = attempt == 0 ? first : full;
+      knn_reset(key, fill, bound, lane, b0);
+      for (int s = 0; s < 27; ++s) {
+        const int sb = __shfl_sync(0xffffffffu, rb, s), se = __shfl_sync(0xffffffffu, re, s);
+        knn_scan_range(key, fill, bound, k, xyz, sb, se, px, py, pz, lane);
+      }
+      got = knn_finish(key, fill, k, dk2, lane);
+      if (got == k || b0 >= full) break;
     }
-    float dk2;
-    got = knn_finish(key, fill, k, dk2, lane);
     exact = got == k && dk2 <= hl * hl;
     if (exact || l + 1 == L) break;
   }
