@@ -193,24 +193,35 @@ def build_halo_plan(level_keys: List[torch.Tensor], owner: List[torch.Tensor], o
         want.append(torch.cat(rows) if rows else torch.zeros((0, 2), dtype=torch.int64, device=dev))
         recv_idx.append(torch.cat(idx) if idx else empty)
     asked = all_to_all_rows(want, group)                               # asked[s]: what rank s wants from me
-    send_idx = []
+    send_idx, answers = [], []
     for s in range(world):
         req = asked[s]
         if s == rank or req.shape[0] == 0:
             send_idx.append(empty)
+            answers.append(torch.zeros((0, 1), dtype=torch.int64, device=dev))
             continue
-        parts = torch.empty(req.shape[0], dtype=torch.long, device=dev)
+        parts = torch.zeros(req.shape[0], dtype=torch.long, device=dev)
+        found = torch.zeros(req.shape[0], dtype=torch.bool, device=dev)
         for l, keys in enumerate(level_keys):
             m = req[:, 0] == l
-            if not bool(m.any()):
+            if keys.numel() == 0 or not bool(m.any()):
                 continue
             k = req[m, 1]
-            pos = torch.searchsorted(keys, k).clamp(max=max(keys.numel() - 1, 0))
-            if keys.numel() == 0 or not bool((keys[pos] == k).all()):
-                raise _lib.NksrError(f"rank {s} asks rank {rank} for voxels it does not hold on level {l}: "
-                                     "halo too thin for this hierarchy")
+            pos = torch.searchsorted(keys, k).clamp(max=keys.numel() - 1)
+            hit = keys[pos] == k
             parts[m] = pos + offsets[l]
-        send_idx.append(parts)
+            found[m] = hit
+        # A halo voxel the owner does not hold: both ranks built their hierarchy from the same points EXCEPT at the
+        # outer rim of the requester's halo, where a per-rank preprocess (kNN normals + grazing filter on truncated
+        # neighbourhoods) may keep a point the owner dropped.  Such voxels are many coarse voxels away from any row the
+        # requester owns, so they are simply left out of the exchange (their entries stay zero); a voxel missing close
+        # to the slab would mean the halo is too thin, which the thickness check of reconstruct_global guards.
+        send_idx.append(parts[found])
+        answers.append(found.to(torch.int64).reshape(-1, 1))
+    replies = all_to_all_rows(answers, group)                          # replies[r]: which of my requests rank r serves
+    for r in range(world):
+        if r != rank and recv_idx[r].numel():
+            recv_idx[r] = recv_idx[r][replies[r].reshape(-1).bool()]
     return HaloPlan(send_idx, recv_idx, group)
 
 

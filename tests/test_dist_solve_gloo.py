@@ -33,6 +33,24 @@ def _worker(rank, world, port, out):
         plan.exchange(vec)
         assert torch.equal(vec, truth), (rank, (vec != truth).nonzero().reshape(-1)[:5])
         assert sum(i.numel() for i in plan.recv_idx) == int((~owned).sum())
+        # a rim voxel only ONE side holds (a per-rank preprocess may keep a point the owner dropped at the outer edge of
+        # the requester's halo): the join leaves it out instead of failing, its entry keeps the caller's value
+        if rank == 0:
+            k0r = torch.cat([keys0, torch.tensor([1000], dtype=torch.int64)])      # key 1000: owned by rank 1, unknown there
+        else:
+            k0r = keys0
+        own_r = [ds.owner_of(k0r.double() + 0.5, bounds), owner[1]]
+        plan_r = ds.build_halo_plan([k0r, keys1], own_r, [0, k0r.numel()])
+        truth_r = torch.cat([k0r.float() * 3.0, 1000.0 + keys1.float() * 7.0])
+        owned_r = torch.cat([o == rank for o in own_r])
+        vec_r = torch.where(owned_r, truth_r, torch.full_like(truth_r, -1.0))
+        plan_r.exchange(vec_r)
+        if rank == 0:
+            assert vec_r[k0r.numel() - 1] == -1.0                                  # untouched
+            keep = torch.ones_like(vec_r, dtype=torch.bool); keep[k0r.numel() - 1] = False
+            assert torch.equal(vec_r[keep], truth_r[keep])
+        else:
+            assert torch.equal(vec_r, truth_r)
         # global dot product over owned entries = dot over the union exactly once
         s = ds._gsum(truth.double() * owned, None)
         ref = (torch.arange(0, 100).double() * 3.0).sum() + (1000.0 + torch.arange(0, 50).double() * 7.0).sum()
