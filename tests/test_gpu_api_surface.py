@@ -79,3 +79,21 @@ def test_headless_example_runs():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-800:]
     assert os.path.getsize("/tmp/recons_simple.obj") > 10000
+
+
+def test_fields_follow_their_tensors_device():
+    """every C-ABI call must run on the device that owns its tensors, not on the current one.
+    Needs two GPUs (skipped on a one-GPU box): reconstruct + mesh on cuda:1 while cuda:0 is current."""
+    import nksr_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tests import clouds
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:1")
+    xyz, nrm = clouds.sphere(6000, noise=0.001)
+    rec = nksr_b200.Reconstructor(dev)
+    field = rec.reconstruct(torch.from_numpy(xyz).to(dev), torch.from_numpy(nrm).to(dev), voxel_size=0.05)
+    assert field.alpha.device == dev and torch.cuda.current_device() == 0
+    mesh = field.extract_dual_mesh(mise_iter=1)
+    r = mesh.v.norm(dim=1)
+    assert mesh.v.device == dev and mesh.f.shape[0] > 500 and abs(float(r.median()) - 0.35) < 0.01
