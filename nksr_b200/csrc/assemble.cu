@@ -376,9 +376,8 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
         }
       }
     } else {
-      // MINB == 3 ("wide" variant, NKSR_FILL_VARIANT=wide): 85 registers, two normal locations = 30 line loads in
-      // flight per warp instead of 15, three blocks per SM instead of four
-#pragma unroll(MINB == 3 ? 2 : 1)
+      // (a "wide" variant -- 80 registers, three blocks per SM, two normal locations = 30 line loads in flight per warp
+      // -- was measured at 187 ms against 175 ms, r2l, and removed)
       for (int q = nb; q < ne; ++q) {
         const float* p0 = cs.e_nrm + ((int64_t)q * L + l) * (3 * NKSR_ROW_STRIDE);
         const float* t = cs.t_nrm + (int64_t)q * 3;
@@ -708,11 +707,8 @@ int launch_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_const
                                                                            rhs, diag, cursor, place)
   // 4 resident blocks per SM (64 registers) for depth <= 4; 5 blocks (48 registers) was measured
   // 1.7x slower (register starvation cuts the loads in flight per warp)
-  static const bool wide = [] { const char* v = getenv("NKSR_FILL_VARIANT"); return v && v[0] == 'w'; }();
   if (svh->depth <= 4) {
-    if (c->nrm_compact) NKSR_FILL(true, 4, 4);
-    else if (wide) NKSR_FILL(false, 4, 3);
-    else NKSR_FILL(false, 4, 4);
+    if (c->nrm_compact) NKSR_FILL(true, 4, 4); else NKSR_FILL(false, 4, 4);
   } else {
     if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH, 2); else NKSR_FILL(false, NKSR_MAX_DEPTH, 2);
   }

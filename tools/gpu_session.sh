@@ -34,6 +34,3 @@ if has spmvncu; then
   timeout 600 ncu --set full --clock-control none -k regex:"k_spmv_stream|k_spmv" -c 6 -o /tmp/${TAG}_spmv python tools/profile_run.py cfg4_outdoor_10M > gpurun_out/${TAG}_spmv_ncu.log 2>&1
   ncu -i /tmp/${TAG}_spmv.ncu-rep --page raw --csv > gpurun_out/${TAG}_spmv_raw.csv 2>/dev/null
 fi
-if has wide; then
-  NKSR_FILL_VARIANT=wide timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mesh > gpurun_out/${TAG}_bench_wide.json 2> gpurun_out/${TAG}_bench_wide.err
-fi
