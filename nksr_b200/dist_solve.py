@@ -282,6 +282,7 @@ def reconstruct_global(reconstructor, xyz: torch.Tensor, normal: Optional[torch.
     xyz = xyz.detach().to(dev, torch.float32).contiguous()
     normal = normal.detach().to(dev, torch.float32).contiguous() if normal is not None else None
     sensor = sensor.detach().to(dev, torch.float32).contiguous() if sensor is not None else None
+    tm = _lib.StageTimer(dev)                      # CUDA-event marks (NKSR_STAGE_TIMES=1), read by bench.py
     L = reconstructor.tree_depth
     w_top = float(voxel_size) * (2 ** (L - 1))
     lo_hi = torch.stack([xyz.min(dim=0).values, -xyz.max(dim=0).values]) if xyz.shape[0] else \
@@ -308,9 +309,11 @@ def reconstruct_global(reconstructor, xyz: torch.Tensor, normal: Optional[torch.
     lx = routed[0].contiguous()
     ln = routed[1].contiguous() if normal is not None else None
     lsens = routed[-1].contiguous() if sensor is not None else None
+    tm.mark("bounds_and_point_routing")
     if preprocess_fn is not None:
         lx, ln, lsens = preprocess_fn(lx, ln, lsens)
         lx = lx.contiguous()
+    tm.mark("preprocess")
     if ln is not None:
         feat = ln
     elif lsens is not None:
@@ -326,6 +329,7 @@ def reconstruct_global(reconstructor, xyz: torch.Tensor, normal: Optional[torch.
     enc = net.encoder(lx, feat, svh, 0)
     feats, dec_svh, _ = net.unet(enc, svh, adaptive_depth=reconstructor.adaptive_depth)
     field = KernelField(dec_svh, net.interpolators, feats.basis_features, approx_kernel_grad)
+    tm.mark("svh_and_network")
     ad = min(reconstructor.adaptive_depth, L)
     offs = dec_svh.offsets
     # ownership of every unknown / normal location by voxel-centre coordinate (exact: integer ijk)
@@ -346,8 +350,12 @@ def reconstruct_global(reconstructor, xyz: torch.Tensor, normal: Optional[torch.
     from .reconstructor import NORMAL_WEIGHT, POS_WEIGHT
     sysm = field.assemble(lx, normal_xyz, -normal_value, POS_WEIGHT / n_points_global,
                           NORMAL_WEIGHT / k_global * (float(voxel_size) ** 2), 1.0)
+    tm.mark("ownership_and_assembly")
     plan = build_halo_plan(dec_svh.keys, owner, offs, group)
+    tm.mark("halo_plan")
     alpha, info = pcg_distributed(sysm, owned, plan, solver_tol, solver_max_iter, 16, group)
+    tm.mark("pcg")
+    field._stage_timer = tm
     field.alpha = alpha
     field.owned = owned
     field.owned_cells = owner[0] == rank
