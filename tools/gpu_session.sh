@@ -34,3 +34,7 @@ if has spmvncu; then
   timeout 600 ncu --set full --clock-control none -k regex:"k_spmv_stream|k_spmv" -c 6 -o /tmp/${TAG}_spmv python tools/profile_run.py cfg4_outdoor_10M > gpurun_out/${TAG}_spmv_ncu.log 2>&1
   ncu -i /tmp/${TAG}_spmv.ncu-rep --page raw --csv > gpurun_out/${TAG}_spmv_raw.csv 2>/dev/null
 fi
+if has global; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_dcg|k_gather|k_scatter|k_reduce|k_spmv" -c 200 --csv --log-file gpurun_out/${TAG}_global_launches.csv python tools/profile_global.py > gpurun_out/${TAG}_global.log 2>&1
+  timeout 300 python tools/profile_global.py > gpurun_out/${TAG}_global_plain.log 2>&1
+fi
