@@ -436,7 +436,9 @@ int nksr_spmv_stream(const int64_t* rowptr, const int32_t* col, const float* val
 namespace {
 
 // w = A u on the OWNED rows (others: w = 0); partials of (r,u), (w,u), (r,r) over the owned rows
-__global__ void __launch_bounds__(kBlock)
+// (8 resident blocks per SM = 32 registers: the persistent 148 x 8 grid must fit in one wave -- at 40 registers it ran
+// in two, 12.1 ms per launch instead of 7.5, r2o)
+__global__ void __launch_bounds__(kBlock, 8)
 k_dcg_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
            const uint8_t* __restrict__ owned, const float* __restrict__ r, const float* __restrict__ u,
            float* __restrict__ w, int64_t n, double* __restrict__ part, const PcgCtrl* __restrict__ ctrl) {
