@@ -38,3 +38,10 @@ if has global; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_dcg|k_gather|k_scatter|k_reduce|k_spmv" -c 200 --csv --log-file gpurun_out/${TAG}_global_launches.csv python tools/profile_global.py > gpurun_out/${TAG}_global.log 2>&1
   timeout 300 python tools/profile_global.py > gpurun_out/${TAG}_global_plain.log 2>&1
 fi
+if has final; then
+  (time timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8) > gpurun_out/${TAG}_pytest.log 2>&1
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1
+  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
+  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+  tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_smoke.log | tail -2; tail -c 600 gpurun_out/${TAG}_bench_reference.json
+fi
