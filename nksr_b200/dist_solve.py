@@ -99,9 +99,10 @@ def slab_bounds(coord: torch.Tensor, world: int, quantum: float, group=None) -> 
         parts = [torch.empty_like(sample) for _ in range(dist.get_world_size(group))]
         dist.all_gather(parts, sample, group=group)
         sample = torch.cat(parts)
-    sample = sample[~torch.isnan(sample)].cpu()
-    qs = torch.quantile(sample, torch.linspace(0, 1, world + 1, dtype=torch.float64)[1:-1])
-    inner = [round(float(q) / quantum) * quantum for q in qs]
+    # (quantiles on the device the sample lives on: sorting world x 131 072 doubles on the host cost ~20 ms at 4 ranks)
+    sample = sample[~torch.isnan(sample)]
+    qs = torch.quantile(sample, torch.linspace(0, 1, world + 1, dtype=torch.float64, device=sample.device)[1:-1])
+    inner = [round(float(q) / quantum) * quantum for q in qs.tolist()]
     for i in range(1, len(inner)):                         # strictly increasing
         inner[i] = max(inner[i], inner[i - 1] + quantum)
     return [-float("inf")] + inner + [float("inf")]
