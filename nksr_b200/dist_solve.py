@@ -220,10 +220,19 @@ def build_halo_plan(level_keys: List[torch.Tensor], owner: List[torch.Tensor], o
         send_idx.append(parts[found])
         answers.append(found.to(torch.int64).reshape(-1, 1))
     replies = all_to_all_rows(answers, group)                          # replies[r]: which of my requests rank r serves
+    asked_total, dropped = 0, 0
     for r in range(world):
         if r != rank and recv_idx[r].numel():
-            recv_idx[r] = recv_idx[r][replies[r].reshape(-1).bool()]
-    return HaloPlan(send_idx, recv_idx, group)
+            ok = replies[r].reshape(-1).bool()
+            asked_total += int(ok.numel())
+            dropped += int((~ok).sum().item())
+            recv_idx[r] = recv_idx[r][ok]
+    if dropped > 0.02 * max(asked_total, 1) + 64:
+        raise _lib.NksrError(f"rank {rank}: {dropped} of {asked_total} halo voxels are unknown to their owners -- more than "
+                             "the rim of a per-rank preprocess explains: the ranks built different hierarchies")
+    plan = HaloPlan(send_idx, recv_idx, group)
+    plan.dropped = dropped
+    return plan
 
 
 def _gsum(t: torch.Tensor, group) -> torch.Tensor:
@@ -362,7 +371,8 @@ def reconstruct_global(reconstructor, xyz: torch.Tensor, normal: Optional[torch.
     field.owned_cells = owner[0] == rank
     field.solve_info = dict(info, n=sysm.n, nnz=sysm.nnz, n_owned=int(owned.sum().item()),
                             halo_recv=int(sum(plan.recv_counts)), halo_send=int(sum(plan.send_counts)),
-                            halo_bytes_per_exchange=plan.bytes_per_exchange, slab=(lo, hi), axis=axis,
+                            halo_bytes_per_exchange=plan.bytes_per_exchange, halo_dropped=getattr(plan, "dropped", 0),
+                            slab=(lo, hi), axis=axis,
                             points_local=int(lx.shape[0]), points_global=int(n_points_global))
     field.set_mask_field(LayerField(dec_svh, ad))
     return field
