@@ -309,6 +309,8 @@ class KernelField(BaseField):
         # are reduced once per voxel (nksr_gram_blocks) and the matrix rows only gather block lines
         cs.mblocks, cs.split_level = None, svh.depth
         split = self.solver_config.get("block_split_level", None)
+        if split is None and os.environ.get("NKSR_BLOCK_SPLIT"):
+            split = int(os.environ["NKSR_BLOCK_SPLIT"])
         # (allocator bookkeeping only: cudaMemGetInfo costs tens of milliseconds next to large allocations)
         free_bytes = _total_memory(dev) - torch.cuda.memory_allocated(dev)
         budget = free_bytes - 1.25 * (8.0 * nnz + 64.0 * n)          # leave room for the CSR arrays + PCG vectors

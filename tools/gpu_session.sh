@@ -45,3 +45,6 @@ if has final; then
   timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
   tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_smoke.log | tail -2; tail -c 600 gpurun_out/${TAG}_bench_reference.json
 fi
+if has split1; then
+  NKSR_BLOCK_SPLIT=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mesh > gpurun_out/${TAG}_bench_split1.json 2> gpurun_out/${TAG}_bench_split1.err
+fi
