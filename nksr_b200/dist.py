@@ -80,11 +80,22 @@ def reconstruct_distributed(reconstructor, xyz: torch.Tensor, normal: Optional[t
         v, f = gather_mesh(torch.zeros((0, 3), device=xyz.device),
                            torch.zeros((0, 3), dtype=torch.int64, device=xyz.device), 0, group)
         return None, (None if v is None else DualMesh(v=v, f=f, c=None))
-    field = reconstructor._reconstruct_chunks(
-        xyz, normal, sensor, DEFAULT_VOXEL_SIZE, float(chunk_size), preprocess_fn,
-        solver_kwargs.get("approx_kernel_grad", False), solver_kwargs.get("solver_tol", 1e-5),
-        solver_kwargs.get("fused_mode", True), solver_kwargs.get("solver_max_iter", 2000),
-        chunk_filter=lambda k, n: owner[k] == rank)
-    mesh = field.extract_dual_mesh(mise_iter=mise_iter)
-    v, f = gather_mesh(mesh.v, mesh.f, 0, group)
-    return field, (None if v is None else type(mesh)(v=v, f=f, c=None))
+    # a rank that fails (e.g. none of its chunks holds enough points) must still enter the collectives, or the others
+    # hang in the gather: contribute an empty piece, then re-raise
+    field, err = None, None
+    try:
+        field = reconstructor._reconstruct_chunks(
+            xyz, normal, sensor, DEFAULT_VOXEL_SIZE, float(chunk_size), preprocess_fn,
+            solver_kwargs.get("approx_kernel_grad", False), solver_kwargs.get("solver_tol", 1e-5),
+            solver_kwargs.get("fused_mode", True), solver_kwargs.get("solver_max_iter", 2000),
+            chunk_filter=lambda k, n: owner[k] == rank)
+        mesh = field.extract_dual_mesh(mise_iter=mise_iter)
+        lv, lf = mesh.v, mesh.f
+    except Exception as e:          # noqa: BLE001 -- re-raised below, after the collective
+        err = e
+        lv = torch.zeros((0, 3), device=xyz.device)
+        lf = torch.zeros((0, 3), dtype=torch.int64, device=xyz.device)
+    v, f = gather_mesh(lv, lf, 0, group)
+    if err is not None:
+        raise err
+    return field, (None if v is None else DualMesh(v=v, f=f, c=None))
