@@ -97,6 +97,15 @@ NKSR_API int nksr_pool27(const int32_t* nbr27, const float* in, int64_t n, int c
 /* out[p][c] = sum of in[child][c] over the children of voxel p (n = voxels of the parent level) */
 NKSR_API int nksr_pool_children(const int32_t* child8, const float* in, int64_t n, int channels,
                        float* out, void* stream);
+/* ---- f2: the sparse convolution of NKSRNetwork's encoder / U-Net (models/nksr_net.py:73-78; unet.f_maps,
+ * configs/default/train.yaml:17-18) as a gather-GEMM over the hierarchy's index tables:
+ *   y[i,:] = act(bias + res[i,:] + sum_k [idx[i*K+k] >= 0] x[idx[i*K+k],:] . W[k])      W: K x c_in x c_out, row-major
+ * idx = nbr27[l] (K = 27): 3x3x3 convolution on level l; idx = child8[l+1] (K = 8): stride-2 convolution l -> l+1.
+ * c_in and c_out multiples of 32; bias / res may be NULL; relu: 0/1; tf32: 0 = fp32 FFMA, 1 = mma.sync TF32 (fp32
+ * accumulation, operands rounded to TF32) */
+NKSR_API int nksr_gather_gemm(const float* x, const int32_t* idx, int64_t n_out, int K, const float* W,
+                     const float* bias, const float* res, float* y, int c_in, int c_out, int relu, int tf32,
+                     void* stream);
 /* first/last+1 sorted location of every level-l voxel: range[2*u], range[2*u+1] */
 NKSR_API int nksr_row_ranges(const int32_t* base_l, int64_t m, int32_t* range, int64_t n_l, void* stream);
 
@@ -105,7 +114,9 @@ NKSR_API int nksr_row_ranges(const int32_t* base_l, int64_t m, int32_t* range, i
  *   mode 0: value rows    e[(m*L + l)*32 + s]             (position constraints)
  *   mode 1: gradient rows e[((m*L + l)*3 + a)*32 + s]     (normal constraints)
  *   mode 2: compact gradient rows e[(m*L + l)*32 + s], s<27: <phi,z_s>, s=27..29: tau
- *           (approx_kernel_grad only; the assembly rebuilds the three rows)              */
+ *           (approx_kernel_grad only; the assembly rebuilds the three rows)
+ *   mode | 4 (modes 0 and 1, depth <= 4): interleaved layout, the four levels of a slot are one float4:
+ *           value rows e[(m*32 + s)*4 + l], gradient rows e[((m*3 + a)*32 + s)*4 + l]; levels >= depth are zero */
 NKSR_API int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float* xyz,
                     const int32_t* base, int64_t m, int mode, int approx_kernel_grad, float* e,
                     void* stream);
@@ -132,7 +143,9 @@ typedef struct {
   int64_t n_nrm;
   float w_nrm;
   float w_reg;
-  int32_t nrm_compact;       /* 1: e_nrm holds compact rows [K][L][32] (nksr_build_rows mode 2) */
+  int32_t nrm_compact;       /* row-layout code.  0: e_pos [N][L][32], e_nrm [K][L][3][32];  1: e_nrm holds compact rows
+                              * [K][L][32] (nksr_build_rows mode 2);  2: both arrays interleaved, e_pos [N][32][4 levels],
+                              * e_nrm [K][3][32][4 levels] (nksr_build_rows mode | 4, depth <= 4) */
   /* per-voxel Gram blocks of the coarse levels l >= split_level (nksr_gram_blocks); NULL = none.
    * Block of (level l, voxel u, offset k) starts at (mblock_off[l] + u*(depth-l) + k) * 28*32 floats */
   const float* mblocks;

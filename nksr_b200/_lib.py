@@ -65,6 +65,7 @@ _SIGNATURES = {
     "nksr_row_ranges": ("i", "pqpqp"),
     "nksr_pool27": ("i", "ppqipp"),
     "nksr_pool_children": ("i", "ppqipp"),
+    "nksr_gather_gemm": ("i", "ppqippppiiiip"),
     "nksr_build_rows": ("i", "SFppqiipp"),
     "nksr_build_rows_voxel": ("i", "SFpppqiipp"),
     "nksr_gram_count": ("i", "Sppp"),

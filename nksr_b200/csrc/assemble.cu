@@ -191,7 +191,14 @@ __device__ __forceinline__ void gram_block_update(float (&m)[28], const float* _
   }
 }
 
-template <int MAXL>
+// level c (uniform) of an interleaved row element (four levels per float4)
+__device__ __forceinline__ float level_of(const float4& v, const int c) {
+  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
+// ILV: rows in the interleaved layout [location][rows][32][4 levels] (nksr_build_rows mode | 4, depth <= 4): one 128-bit
+// load per (location, axis) brings both lines of the block
+template <int MAXL, bool ILV>
 __global__ void __launch_bounds__(kWarps * 32)
 k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks) {
   __shared__ __align__(16) float stage[kWarps][3][32];
@@ -212,9 +219,16 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
     const int32_t* rp = cs.range_pos + 2 * (svh.offset[l] + u);
     const int pb = __ldg(rp), pe = __ldg(rp + 1);
     for (int q = pb; q < pe; ++q) {
-      const float* p0 = cs.e_pos + ((int64_t)q * L + l) * NKSR_ROW_STRIDE + lane;
-      const float e0 = __ldg(p0);
-      const float ek = k == 0 ? e0 : __ldg(p0 + k * NKSR_ROW_STRIDE);
+      float e0, ek;
+      if (ILV) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(cs.e_pos) + (int64_t)q * NKSR_ROW_STRIDE + lane);
+        e0 = level_of(v, l);
+        ek = level_of(v, l + k);
+      } else {
+        const float* p0 = cs.e_pos + ((int64_t)q * L + l) * NKSR_ROW_STRIDE + lane;
+        e0 = __ldg(p0);
+        ek = k == 0 ? e0 : __ldg(p0 + k * NKSR_ROW_STRIDE);
+      }
       stage[wid][0][lane] = cs.w_pos * e0;
       __syncwarp();
       gram_block_update(m, stage[wid][0], ek);
@@ -230,9 +244,16 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
       float ek[3];
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) {
-        const float e0 = __ldg(p0 + ax * NKSR_ROW_STRIDE);
+        float e0;
+        if (ILV) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(cs.e_nrm) + ((int64_t)q * 3 + ax) * NKSR_ROW_STRIDE + lane);
+          e0 = level_of(v, l);
+          ek[ax] = level_of(v, l + k);
+        } else {
+          e0 = __ldg(p0 + ax * NKSR_ROW_STRIDE);
+          ek[ax] = k == 0 ? e0 : __ldg(p0 + (k * 3 + ax) * NKSR_ROW_STRIDE);
+        }
         const float el = cs.w_nrm * e0;
-        ek[ax] = k == 0 ? e0 : __ldg(p0 + (k * 3 + ax) * NKSR_ROW_STRIDE);
         if (k == 0) bvec = fmaf(el, __ldg(cs.t_nrm + (int64_t)q * 3 + ax), bvec);
         stage[wid][ax][lane] = el;
       }
@@ -248,7 +269,11 @@ k_gram_blocks(nksr_svh_t svh, nksr_constraints_t cs, float* __restrict__ mblocks
   blk[27 * NKSR_ROW_STRIDE + lane] = bvec;
 }
 
-template <bool COMPACT, int MAXL, int MINB, bool PLACED>
+// ILV (MAXL == 4): rows in the interleaved layout -- one 128-bit load per lane brings the four levels of a location
+// (value rows) or of one axis of it (gradient rows): 1 + 3 wide loads per visited location instead of 4 + 12 narrow ones
+// (r2f: 13.6 G load requests, the LSU the busiest unit of the kernel).  Same products in the same order: the matrix is
+// bitwise the one of the plain layout.
+template <bool COMPACT, int MAXL, int MINB, bool PLACED, bool ILV>
 __global__ void __launch_bounds__(kWarps * 32, MINB)
 k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_total,
             const int32_t* __restrict__ cnt, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col_out,
@@ -332,6 +357,36 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
       for (int k = 0; k < MAXL; ++k)
         if (k <= nup) r[k] = __ldg(blk + (int64_t)k * kBlockFloats + si * NKSR_ROW_STRIDE + lane);
     } else {
+    if (ILV) {
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);     // ABSOLUTE levels 0,1 | 2,3
+      const float4* ep = reinterpret_cast<const float4*>(cs.e_pos) + lane;
+      for (int q = pb; q < pe; ++q) {
+        const float4 v = __ldg(ep + (int64_t)q * NKSR_ROW_STRIDE);
+        const float a = cs.w_pos * __shfl_sync(0xffffffffu, level_of(v, l), si);
+        a01 = __ffma2_rn(make_float2(a, a), make_float2(v.x, v.y), a01);
+        a23 = __ffma2_rn(make_float2(a, a), make_float2(v.z, v.w), a23);
+      }
+      const float4* en = reinterpret_cast<const float4*>(cs.e_nrm) + lane;
+      for (int q = nb; q < ne; ++q) {
+        const float4* p = en + (int64_t)q * (3 * NKSR_ROW_STRIDE);
+        // own coefficients: broadcast loads of level l of slot si (see the note in the plain loop below)
+        const float* ps = cs.e_nrm + ((int64_t)q * (3 * NKSR_ROW_STRIDE) + si) * 4 + l;
+        const float* t = cs.t_nrm + (int64_t)q * 3;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          const float a = cs.w_nrm * __ldg(ps + ax * (4 * NKSR_ROW_STRIDE));
+          bsum = fmaf(a, __ldg(t + ax), bsum);
+          const float4 v = __ldg(p + ax * NKSR_ROW_STRIDE);
+          a01 = __ffma2_rn(make_float2(a, a), make_float2(v.x, v.y), a01);
+          a23 = __ffma2_rn(make_float2(a, a), make_float2(v.z, v.w), a23);
+        }
+      }
+      // absolute -> relative levels (l is uniform in the warp)
+      if (l == 0) { r[0] = a01.x; r[1] = a01.y; r[2] = a23.x; r[3] = a23.y; }
+      else if (l == 1) { r[0] = a01.y; r[1] = a23.x; r[2] = a23.y; }
+      else if (l == 2) { r[0] = a23.x; r[1] = a23.y; }
+      else { r[0] = a23.y; }
+    } else {
     // packed fp32 FMAs (FFMA2, sm_100): two levels per instruction, same IEEE result per lane
     float2 r2[MAXL / 2];
 #pragma unroll
@@ -400,6 +455,7 @@ k_gram_fill(nksr_svh_t svh, nksr_feat_t feat, nksr_constraints_t cs, int64_t n_t
     }
 #pragma unroll
     for (int k2 = 0; k2 < MAXL / 2; ++k2) { r[2 * k2] += r2[k2].x; r[2 * k2 + 1] += r2[k2].y; }
+    }  // !ILV
     }  // !use_blocks
     // flush: every lane < 27 owns a distinct structural slot per level; slot = base of the source voxel (computed once
     // per row by lane `us`, see flush_base above) + constant of the lane.  (r2b source page: the per-lane index
@@ -675,16 +731,20 @@ int64_t nksr_gram_block_floats(const nksr_svh_t* svh, int split_level) {
 }
 
 int nksr_gram_blocks(const nksr_svh_t* svh, const nksr_constraints_t* c, float* mblocks, void* stream) {
-  if (!svh || !c || !mblocks || c->nrm_compact || c->split_level < 0 || c->split_level > svh->depth)
+  if (!svh || !c || !mblocks || c->nrm_compact == 1 || c->split_level < 0 || c->split_level > svh->depth)
     return NKSR_E_INVALID;
+  const bool ilv = c->nrm_compact == 2;               // interleaved rows (both arrays), depth <= 4
+  if (ilv && svh->depth > 4) return NKSR_E_INVALID;
   int64_t warps = 0;
   for (int l = c->split_level; l < svh->depth; ++l) warps += svh->n[l] * (svh->depth - l);
   if (warps == 0) return NKSR_OK;
   const int grid = grid_for(warps, kWarps);
-  if (svh->depth <= 4)
-    k_gram_blocks<4><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
+  if (ilv)
+    k_gram_blocks<4, true><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
+  else if (svh->depth <= 4)
+    k_gram_blocks<4, false><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
   else
-    k_gram_blocks<NKSR_MAX_DEPTH><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
+    k_gram_blocks<NKSR_MAX_DEPTH, false><<<grid, kWarps * 32, 0, as_stream(stream)>>>(*svh, *c, mblocks);
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }
@@ -703,15 +763,18 @@ int launch_fill(const nksr_svh_t* svh, const nksr_feat_t* feat, const nksr_const
   cudaStream_t s = as_stream(stream);
   const size_t smem = (size_t)kWarps * kMaxSlots * sizeof(float);
   const int grid = grid_for(n, kWarps);
-#define NKSR_FILL(COMPACT, MAXL, MINB)                                                                       \
-  k_gram_fill<COMPACT, MAXL, MINB, PLACED><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, val, \
-                                                                           rhs, diag, cursor, place)
+#define NKSR_FILL(COMPACT, MAXL, MINB, ILV)                                                                  \
+  k_gram_fill<COMPACT, MAXL, MINB, PLACED, ILV><<<grid, kWarps * 32, smem, s>>>(*svh, *feat, *c, n, cnt, rowptr, col, \
+                                                                                val, rhs, diag, cursor, place)
   // 4 resident blocks per SM (64 registers) for depth <= 4; 5 blocks (48 registers) was measured
   // 1.7x slower (register starvation cuts the loads in flight per warp)
-  if (svh->depth <= 4) {
-    if (c->nrm_compact) NKSR_FILL(true, 4, 4); else NKSR_FILL(false, 4, 4);
+  if (c->nrm_compact == 2) {                          // interleaved rows
+    if (svh->depth > 4) return NKSR_E_INVALID;
+    NKSR_FILL(false, 4, 4, true);
+  } else if (svh->depth <= 4) {
+    if (c->nrm_compact) NKSR_FILL(true, 4, 4, false); else NKSR_FILL(false, 4, 4, false);
   } else {
-    if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH, 2); else NKSR_FILL(false, NKSR_MAX_DEPTH, 2);
+    if (c->nrm_compact) NKSR_FILL(true, NKSR_MAX_DEPTH, 2, false); else NKSR_FILL(false, NKSR_MAX_DEPTH, 2, false);
   }
 #undef NKSR_FILL
   NKSR_CHECK_LAUNCH();

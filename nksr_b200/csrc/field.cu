@@ -14,7 +14,10 @@ constexpr int kWarpsPerBlock = 8;
 // One warp per LOCATION, all levels in one (unrolled) loop: the point is read once, the per-level
 // dependent chains (base -> key -> neighbours -> features) of the levels overlap, and the grid
 // has L times fewer blocks than a warp per (location, level).
-template <int MODE, int MAXL>
+// ILV (depth <= 4): "levels in the lane" layout -- the four levels of one (location, axis, slot) are one float4,
+// [m][rows][32 slots][4 levels]: the assembly reads all levels of a location with ONE 128-bit load per lane (512
+// contiguous bytes per warp) instead of one 32-bit load per level, and this kernel writes them with one 128-bit store.
+template <int MODE, int MAXL, bool ILV>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, const int32_t* __restrict__ base,
              int64_t m, bool fullgrad, float* __restrict__ e) {
@@ -34,19 +37,29 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
   // location-major layout [m][L][rows][32]: all lines of one location are contiguous, so the
   // assembly kernel reaches them with compile-time offsets from one base pointer
   float* out0 = e + (int64_t)i * svh.depth * ROWS * NKSR_ROW_STRIDE;
+  float kv[MAXL][ROWS];            // ILV only: the levels of this lane's slot (dead code otherwise)
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l)
+#pragma unroll
+    for (int a = 0; a < ROWS; ++a) kv[l][a] = 0.f;
 #pragma unroll
   for (int l = 0; l < MAXL; ++l) {
     if (l < svh.depth) {
       float* out = out0 + l * ROWS * NKSR_ROW_STRIDE;
       const int b = __ldg(base + (int64_t)l * m + i);
       if (b < 0) {
-        out[lane] = 0.f;
-        if (GRAD) { out[32 + lane] = 0.f; out[64 + lane] = 0.f; }
+        if (!ILV) {
+          out[lane] = 0.f;
+          if (GRAD) { out[32 + lane] = 0.f; out[64 + lane] = 0.f; }
+        }
       } else {
         const float wl = svh.voxel_size * (float)(1 << l);
         LaneKernel r = eval_level_lane<GRAD>(svh.nbr27[l], feat.z[l], feat.channels, l, wl, inv0, px, py, pz, b,
                                              hx >> (l + 1), hy >> (l + 1), hz >> (l + 1), fullgrad, lane);
-        if (GRAD) {
+        if (ILV) {
+#pragma unroll
+          for (int a = 0; a < ROWS; ++a) kv[l][a] = GRAD ? r.dk[a] : r.k;
+        } else if (GRAD) {
           out[lane] = r.dk[0];
           out[32 + lane] = r.dk[1];
           out[64 + lane] = r.dk[2];
@@ -57,6 +70,12 @@ k_build_rows(nksr_svh_t svh, nksr_feat_t feat, const float* __restrict__ xyz, co
         }
       }
     }
+  }
+  if (ILV) {
+    float4* o4 = reinterpret_cast<float4*>(e) + ((int64_t)i * ROWS) * NKSR_ROW_STRIDE + lane;
+#pragma unroll
+    for (int a = 0; a < ROWS; ++a)
+      o4[a * NKSR_ROW_STRIDE] = make_float4(kv[0][a], kv[1 % MAXL][a], kv[2 % MAXL][a], kv[3 % MAXL][a]);
   }
 }
 
@@ -347,11 +366,18 @@ int nksr_build_rows(const nksr_svh_t* svh, const nksr_feat_t* feat, const float*
   if (m == 0) return NKSR_OK;
   const int grid = grid_for(m, kWarpsPerBlock);
   cudaStream_t s = as_stream(stream);
+  // mode | 4: the interleaved layout [m][rows][32][4 levels] (value and gradient rows, depth <= 4)
+  const bool ilv = (mode & 4) != 0;
+  mode &= ~4;
   if (mode < 0 || mode > 2 || (mode == 2 && !approx_kernel_grad)) return NKSR_E_INVALID;
+  if (ilv && (mode == 2 || svh->depth > 4)) return NKSR_E_INVALID;
   const bool full = mode == 1 && !approx_kernel_grad;
 #define NKSR_ROWS(MODE, MAXL) \
-  k_build_rows<MODE, MAXL><<<grid, kWarpsPerBlock * 32, 0, s>>>(*svh, *feat, xyz, base, m, full, e)
-  if (svh->depth <= 4) {
+  k_build_rows<MODE, MAXL, false><<<grid, kWarpsPerBlock * 32, 0, s>>>(*svh, *feat, xyz, base, m, full, e)
+  if (ilv) {
+    if (mode == 0) k_build_rows<0, 4, true><<<grid, kWarpsPerBlock * 32, 0, s>>>(*svh, *feat, xyz, base, m, full, e);
+    else k_build_rows<1, 4, true><<<grid, kWarpsPerBlock * 32, 0, s>>>(*svh, *feat, xyz, base, m, full, e);
+  } else if (svh->depth <= 4) {
     if (mode == 0) NKSR_ROWS(0, 4); else if (mode == 1) NKSR_ROWS(1, 4); else NKSR_ROWS(2, 4);
   } else {
     if (mode == 0) NKSR_ROWS(0, NKSR_MAX_DEPTH); else if (mode == 1) NKSR_ROWS(1, NKSR_MAX_DEPTH);

@@ -414,6 +414,7 @@ int nksr_gram_fill_grouped(const nksr_svh_t* svh, const nksr_feat_t* feat, const
                            const int32_t* cnt, const int64_t* rowptr, const nksr_placement_t* placement,
                            int32_t* col, float* val, float* rhs, float* diag, void* stream) {
   if (!svh || !feat || !c || !placement || svh->depth < 1) return NKSR_E_INVALID;
+  if (c->nrm_compact == 2) return NKSR_E_INVALID;     // the interleaved row layout belongs to the row fill
   // needs the virtual level above the coarsest one (parent tables on every level) and at most 4 levels
   if (svh->depth > 4 || svh->depth >= NKSR_MAX_DEPTH || !svh->parent[svh->depth - 1] || !svh->child8[svh->depth] ||
       !svh->nbr27[svh->depth])

@@ -30,6 +30,8 @@ from .svh import SparseFeatureHierarchy
 # "structural" = straight to the final slot from prefix tables (SPEC S6b).  solver_config['placement'] or the
 # NKSR_PLACEMENT environment variable override it.
 DEFAULT_PLACEMENT = "structural"
+# measured A/B pending on the B200 (r2w): until then the layout every parity test of this round ran on
+DEFAULT_ROW_LAYOUT = "levels"
 
 
 _TOTAL_MEMORY = {}
@@ -85,6 +87,17 @@ def _as_level_list(features, depth):
     if isinstance(features, dict):
         return [features.get(d, None) for d in range(depth)]
     return [features[d] if d < len(features) else None for d in range(depth)]
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """one side stream per device for the life of the process (the caching allocator keeps a pool per stream)"""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(torch.device("cuda", key))
+    return _SIDE_STREAMS[key]
 
 
 class KernelField(BaseField):
@@ -144,8 +157,11 @@ class KernelField(BaseField):
         return self._feat_view
 
     # ------------------------------------------------------------------ solve
-    def _sorted_rows(self, xyz: torch.Tensor, mode: int, extra: Optional[torch.Tensor] = None):
-        """Morton-sort locations, locate them on every level, build their kernel rows."""
+    def _sorted_rows(self, xyz: torch.Tensor, mode: int, extra: Optional[torch.Tensor] = None,
+                     interleaved: bool = False):
+        """Morton-sort locations, locate them on every level, build their kernel rows.
+        `interleaved` (depth <= 4, modes 0 / 1): rows as (m, rows, 32, 4 levels) -- the four levels of a slot are one
+        float4 -- instead of (m, depth, rows * 32)."""
         svh, dev = self.svh, xyz.device
         st = stream_ptr(dev)
         m = xyz.shape[0]
@@ -165,6 +181,13 @@ class KernelField(BaseField):
         for l in range(svh.depth):
             call("nksr_row_ranges", base[l], m, ranges[offs[l]:], svh.num_voxels(l), st)
         width = _lib.ROW_STRIDE * (3 if mode == 1 else 1)
+        if interleaved:
+            if svh.depth > 4 or mode == 2:
+                raise _lib.NksrError("interleaved rows: depth <= 4, value or gradient rows")
+            e = torch.empty((m, width // _lib.ROW_STRIDE, _lib.ROW_STRIDE, 4), dtype=torch.float32, device=dev)
+            call("nksr_build_rows", svh.view(), self.feat_view(), xs, base, m, mode | 4,
+                 int(self.approx_kernel_grad), e, st)
+            return xs, ex, base, ranges, e
         e = torch.empty((m, svh.depth, width), dtype=torch.float32, device=dev)      # location-major
         # 'location' (default): one warp per location (any channel count); 'voxel': one warp per voxel, stencil +
         # features fetched once for all the voxel's locations (bitwise the same rows)
@@ -229,47 +252,12 @@ class KernelField(BaseField):
             self.system = sysm
         return self
 
-    def assemble(self, pos_xyz, normal_xyz=None, normal_value=None, pos_weight=1.0, normal_weight=1.0,
-                 reg_weight=1.0):
-        """Kernel rows + Gram assembly: returns the CSR system (rowptr, col, val, rhs, diag, n, nnz)."""
+    def _count_and_place(self, n, keep):
+        """structure-only part of the assembly (row lengths, placement tables, row pointers): depends on the hierarchy
+        alone, so it may run on a side stream while the kernel rows are built (solver_config['overlap_count'])"""
         svh = self.svh
         dev = svh.device
-        _lib.require_cuda(pos_xyz, "pos_xyz")
         st = stream_ptr(dev)
-        n = svh.num_unknowns
-        if n == 0:
-            raise _lib.NksrError("empty hierarchy: nothing to solve")
-        if n >= 2 ** 31:
-            raise _lib.NksrError("more than 2^31 unknowns: shard the cloud (chunk_size)")
-        pos_xyz = pos_xyz.detach().to(dev, torch.float32).contiguous()
-        cs = _lib.ConstraintsT()
-        keep = []
-        _, _, _, range_pos, e_pos = self._sorted_rows(pos_xyz, 0)
-        keep += [range_pos, e_pos]
-        cs.e_pos, cs.range_pos, cs.n_pos, cs.w_pos = e_pos.data_ptr(), range_pos.data_ptr(), pos_xyz.shape[0], float(pos_weight)
-        if normal_xyz is not None and normal_xyz.shape[0] > 0:
-            normal_xyz = normal_xyz.detach().to(dev, torch.float32).contiguous()
-            normal_value = normal_value.detach().to(dev, torch.float32).contiguous()
-            # approx_kernel_grad: compact gradient rows (one 128 B line per location and level)
-            # compact gradient rows (one line instead of three per location and level) save 2/3 of
-            # the row memory but cost ALU in the assembly; measured slower on B200 (profiles/r1c),
-            # so they are opt-in for clouds that would not fit otherwise
-            compact = self.solver_config.get("compact_rows")
-            if compact is None:
-                compact = os.environ.get("NKSR_COMPACT_ROWS", "0") == "1"
-            nrm_mode = 2 if (self.approx_kernel_grad and compact) else 1
-            _, t_nrm, _, range_nrm, e_nrm = self._sorted_rows(normal_xyz, nrm_mode, normal_value)
-            cs.nrm_compact = int(nrm_mode == 2)
-            keep += [t_nrm, range_nrm, e_nrm]
-            cs.e_nrm, cs.range_nrm, cs.t_nrm = e_nrm.data_ptr(), range_nrm.data_ptr(), t_nrm.data_ptr()
-            cs.n_nrm, cs.w_nrm = normal_xyz.shape[0], float(normal_weight)
-        else:
-            cs.e_nrm = cs.range_nrm = cs.t_nrm = None
-            cs.n_nrm, cs.w_nrm = 0, 0.0
-        cs.w_reg = float(reg_weight)
-
-        tm = getattr(self, "_timer", None) or _lib.StageTimer(dev, enabled=False)
-        tm.mark("kernel_rows")
         cnt = torch.empty(n, dtype=torch.int32, device=dev)
         placement = self.solver_config.get("placement") or os.environ.get("NKSR_PLACEMENT") or DEFAULT_PLACEMENT
         if placement not in ("sorted", "structural"):
@@ -303,6 +291,73 @@ class KernelField(BaseField):
         nb = call("nksr_scan_workspace_bytes", n)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         call("nksr_gram_rowptr", cnt, cnt_down, n, rowptr, ws, nb, st)
+        return cnt, cnt_down, place, rowptr
+
+    def assemble(self, pos_xyz, normal_xyz=None, normal_value=None, pos_weight=1.0, normal_weight=1.0,
+                 reg_weight=1.0):
+        """Kernel rows + Gram assembly: returns the CSR system (rowptr, col, val, rhs, diag, n, nnz)."""
+        svh = self.svh
+        dev = svh.device
+        _lib.require_cuda(pos_xyz, "pos_xyz")
+        st = stream_ptr(dev)
+        n = svh.num_unknowns
+        if n == 0:
+            raise _lib.NksrError("empty hierarchy: nothing to solve")
+        if n >= 2 ** 31:
+            raise _lib.NksrError("more than 2^31 unknowns: shard the cloud (chunk_size)")
+        pos_xyz = pos_xyz.detach().to(dev, torch.float32).contiguous()
+        cs = _lib.ConstraintsT()
+        keep = []
+        # row lengths + placement tables need the hierarchy only: optionally on a side stream, under the row building
+        overlap = self.solver_config.get("overlap_count")
+        if overlap is None:
+            overlap = os.environ.get("NKSR_OVERLAP", "0") == "1"
+        side = None
+        if overlap:
+            side = _side_stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                cnt, cnt_down, place, rowptr = self._count_and_place(n, keep)
+        # row layout.  'interleaved' (depth <= 4, row fill, plain gradient rows): the four levels of a slot are one float4,
+        # so the fill reads a location with 1 + 3 128-bit loads per lane instead of 4 + 12 32-bit ones (csrc/assemble.cu,
+        # ILV); 'levels': one 128-byte line per (location, level, axis).  Both give bitwise the same matrix.
+        layout = self.solver_config.get("row_layout") or os.environ.get("NKSR_ROW_LAYOUT") or DEFAULT_ROW_LAYOUT
+        if layout not in ("interleaved", "levels"):
+            raise ValueError("solver_config['row_layout'] must be 'interleaved' or 'levels'")
+        compact = self.solver_config.get("compact_rows")
+        if compact is None:
+            compact = os.environ.get("NKSR_COMPACT_ROWS", "0") == "1"
+        ilv = (layout == "interleaved" and svh.depth <= 4 and not (self.approx_kernel_grad and compact)
+               and (self.solver_config.get("fill") or os.environ.get("NKSR_FILL") or "rows") == "rows"
+               and (self.solver_config.get("rows") or os.environ.get("NKSR_ROWS") or "location") == "location")
+        _, _, _, range_pos, e_pos = self._sorted_rows(pos_xyz, 0, interleaved=ilv)
+        keep += [range_pos, e_pos]
+        cs.e_pos, cs.range_pos, cs.n_pos, cs.w_pos = e_pos.data_ptr(), range_pos.data_ptr(), pos_xyz.shape[0], float(pos_weight)
+        if normal_xyz is not None and normal_xyz.shape[0] > 0:
+            normal_xyz = normal_xyz.detach().to(dev, torch.float32).contiguous()
+            normal_value = normal_value.detach().to(dev, torch.float32).contiguous()
+            # approx_kernel_grad: compact gradient rows (one 128 B line per location and level)
+            # compact gradient rows (one line instead of three per location and level) save 2/3 of
+            # the row memory but cost ALU in the assembly; measured slower on B200 (profiles/r1c),
+            # so they are opt-in for clouds that would not fit otherwise
+            nrm_mode = 2 if (self.approx_kernel_grad and compact) else 1
+            _, t_nrm, _, range_nrm, e_nrm = self._sorted_rows(normal_xyz, nrm_mode, normal_value, interleaved=ilv)
+            cs.nrm_compact = 2 if ilv else int(nrm_mode == 2)          # the C struct's row-layout code
+            keep += [t_nrm, range_nrm, e_nrm]
+            cs.e_nrm, cs.range_nrm, cs.t_nrm = e_nrm.data_ptr(), range_nrm.data_ptr(), t_nrm.data_ptr()
+            cs.n_nrm, cs.w_nrm = normal_xyz.shape[0], float(normal_weight)
+        else:
+            cs.e_nrm = cs.range_nrm = cs.t_nrm = None
+            cs.n_nrm, cs.w_nrm = 0, 0.0
+            cs.nrm_compact = 2 if ilv else 0
+        cs.w_reg = float(reg_weight)
+
+        tm = getattr(self, "_timer", None) or _lib.StageTimer(dev, enabled=False)
+        tm.mark("kernel_rows")
+        if side is None:
+            cnt, cnt_down, place, rowptr = self._count_and_place(n, keep)
+        else:
+            torch.cuda.current_stream(dev).wait_stream(side)
         nnz = int(rowptr[-1].item())
         tm.mark("gram_count")
         # coarse levels (>= split): a voxel owns hundreds of constraint rows, so their 27x27 products

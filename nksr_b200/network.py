@@ -27,7 +27,8 @@ from torch import nn
 from .svh import SparseFeatureHierarchy
 
 _DEFAULTS = dict(kernel_dim=4, tree_depth=4, adaptive_depth=2, feature="normal",
-                 interpolator=dict(n_hidden=2, hidden_dim=16), udf=dict(enabled=False), seed=0)
+                 interpolator=dict(n_hidden=2, hidden_dim=16), udf=dict(enabled=False), seed=0,
+                 unet=dict(f_maps=32), backbone="pool", precision="fp32")
 
 
 def _get(hp, key, default):
@@ -67,6 +68,12 @@ class NKSRNetwork(nn.Module):
         self.adaptive_depth = int(hp["adaptive_depth"])
         self.feature = hp["feature"]
         self.compute_structure = False
+        # backbone: 'pool' = the geometric stand-in below (sensible output without trained weights: what the benchmark and
+        # the examples use); 'unet' = the sparse-conv encoder / U-Net (nksr_b200/unet.py, csrc/sparse_conv.cu), random init
+        self.backbone = str(hp["backbone"])
+        if self.backbone not in ("pool", "unet"):
+            raise ValueError("backbone: 'pool' or 'unet'")
+        self.tf32 = str(hp["precision"]) == "tf32"
         interp = hp["interpolator"]
         gen = torch.Generator().manual_seed(int(hp["seed"]))
         state = torch.random.get_rng_state()
@@ -80,6 +87,13 @@ class NKSRNetwork(nn.Module):
             self.structure_heads = nn.ModuleList([nn.Linear(4, 3) for _ in range(self.tree_depth)])
             self.sdf_decoder = nn.Sequential(nn.Linear(C, 16), nn.ReLU(), nn.Linear(16, 1))
             self.udf_decoder = nn.Sequential(nn.Linear(C, 16), nn.ReLU(), nn.Linear(16, 1))
+            if self.backbone == "unet":
+                from .unet import PointEncoder, SparseUNet
+                f_maps = int(_get(hp["unet"], "f_maps", 32))
+                if f_maps % 32:
+                    raise ValueError("unet.f_maps must be a multiple of 32 (csrc/sparse_conv.cu stages 32-channel chunks)")
+                self.point_encoder = PointEncoder(0 if self.feature in (None, "none") else 3, f_maps, f_maps)
+                self.backbone_net = SparseUNet(self.tree_depth, f_maps, C)
         finally:
             torch.random.set_rng_state(state)
         del gen
@@ -90,6 +104,10 @@ class NKSRNetwork(nn.Module):
     @torch.no_grad()
     def encoder(self, xyz: torch.Tensor, feat, svh: SparseFeatureHierarchy, depth: int = 0):
         from ._lib import call, stream_ptr
+        if self.backbone == "unet":
+            if feat is None and self.point_encoder.fc_in.in_features > 3:
+                feat = torch.zeros_like(xyz)
+            return SimpleNamespace(svh=svh, x0=self.point_encoder(xyz.to(torch.float32), feat, svh))
         base0 = svh.locate(xyz)[0].long()                               # finest containing voxel
         ones = torch.ones((xyz.shape[0], 1), device=xyz.device)
         src = torch.cat([feat.to(torch.float32) if feat is not None else torch.zeros_like(xyz), ones], dim=1)
@@ -115,6 +133,16 @@ class NKSRNetwork(nn.Module):
     def unet(self, feat, svh: SparseFeatureHierarchy, adaptive_depth: int = None, gt_decoder_svh=None):
         dec_svh = gt_decoder_svh if gt_decoder_svh is not None else svh
         C = self.kernel_dim
+        if self.backbone == "unet":
+            # the decoder runs on the encoder hierarchy; a given decoder hierarchy (ground truth at training time,
+            # models/nksr_net.py:77) receives the features of the voxels it shares with it.  Growing the decoder
+            # hierarchy from the predicted structure logits needs trained weights and is not done here.
+            from .unet import restrict_to
+            o = self.backbone_net(feat.x0, svh, tf32=self.tf32)
+            return (FeatureBundle(basis_features=restrict_to(o.basis, svh, dec_svh),
+                                  normal_features=restrict_to(o.normal, svh, dec_svh),
+                                  structure_features=restrict_to(o.structure, svh, dec_svh),
+                                  udf_features=restrict_to(o.udf, svh, dec_svh)), dec_svh, dec_svh)
         basis, normal, structure, udf = {}, {}, {}, {}
         up = None
         for l in range(svh.depth - 1, -1, -1):

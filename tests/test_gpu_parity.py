@@ -92,6 +92,96 @@ def test_kernel_rows_match_oracle(cuda, C, approx):
             assert np.all(e_np[:, l].reshape(-1, 32)[:, 27:] == 0)
 
 
+@pytest.mark.parametrize("L,C,approx", [(4, 4, False), (4, 4, True), (3, 16, False), (1, 4, True), (2, 3, False)])
+def test_interleaved_rows_are_the_level_rows(cuda, L, C, approx):
+    """nksr_build_rows mode | 4: the rows with the four levels of a slot in one float4 are, value for value (bitwise),
+    the rows of the plain layout; levels the hierarchy does not have are zero."""
+    xyz, _ = clouds.shapenet_like(3000)
+    svh, osvh = _build(cuda, xyz, 0.02, L)
+    field = _field(cuda, svh, _feats(osvh, C, 7), approx)
+    rng = np.random.default_rng(4)
+    q = np.concatenate([xyz[:2000], osvh.centers(0)[:1500],
+                        osvh.centers(0)[:1500] + rng.uniform(-0.4, 0.4, (1500, 3)).astype(np.float32) * 0.02])
+    q = torch.from_numpy(np.ascontiguousarray(q.astype(np.float32))).to(cuda)
+    for mode in (0, 1):
+        _, _, base, _, e = field._sorted_rows(q, mode)
+        _, _, base_i, _, ei = field._sorted_rows(q, mode, interleaved=True)
+        rows = 3 if mode == 1 else 1
+        assert torch.equal(base, base_i) and ei.shape == (q.shape[0], rows, 32, 4)
+        plain = e.reshape(q.shape[0], L, rows, 32).permute(0, 2, 3, 1)             # (m, rows, 32, L)
+        assert torch.equal(ei[..., :L], plain)
+        assert bool((ei[..., L:] == 0).all())
+        assert float(plain.abs().max()) > 0
+
+
+@pytest.mark.parametrize("L,W,approx,split,normals,placement", [
+    (4, 0.02, False, None, True, "structural"),   # automatic split level: blocks on the two coarse levels
+    (4, 0.02, True, None, True, "structural"),
+    (4, 0.02, False, 4, True, "structural"),      # every level through the row loops
+    (4, 0.02, False, 1, True, "structural"),      # blocks from level 1
+    (4, 0.02, False, 0, True, "structural"),      # blocks everywhere
+    (4, 0.02, False, None, True, "sorted"),       # atomic-cursor placement + segment sort
+    (3, 0.03, False, None, True, "structural"),   # a level the layout pads with zeros
+    (1, 0.05, False, None, True, "structural"),
+    (4, 0.02, False, None, False, "structural"),  # position constraints only
+])
+def test_interleaved_layout_gives_the_same_system(cuda, L, W, approx, split, normals, placement):
+    """solver_config['row_layout'] = 'interleaved' (csrc/assemble.cu, ILV: 128-bit loads of all levels of a location)
+    against 'levels': same products in the same order -- row pointers, columns, values, rhs and diagonal are bitwise
+    equal, through the row loops and through the per-voxel blocks."""
+    import nksr_b200
+    xyz, _ = clouds.shapenet_like(3000)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    svh, osvh = _build(cuda, xyz, W, L)
+    feats = _feats(osvh, 4, 5)
+    nxyz = np.concatenate([osvh.centers(d) for d in range(min(2, L))])
+    rng = np.random.default_rng(3)
+    nxyz[::2] += (rng.uniform(-0.3, 0.3, nxyz[::2].shape) * W).astype(np.float32)   # half at the centres, half generic
+    nval = -(nxyz / np.linalg.norm(nxyz, axis=1, keepdims=True)).astype(np.float32)
+    pw, nw = 1e4 / xyz.shape[0], 1e4 / nxyz.shape[0] * W * W
+    out = []
+    for layout in ("levels", "interleaved"):
+        field = _field(cuda, svh, feats, approx)
+        field.solver_config.update(keep_system=True, max_iter=0, row_layout=layout, placement=placement)
+        if split is not None:
+            field.solver_config["block_split_level"] = split
+        if normals:
+            field.solve(t(xyz), t(nxyz), t(nval), pw, nw, 1.0)
+        else:
+            field.solve(t(xyz), None, None, pw, 0.0, 1.0)
+        s_ = field.system
+        out.append([_np(a).copy() for a in (s_.rowptr, s_.col, s_.val, s_.rhs, s_.diag)])
+    assert out[0][0][-1] > 0 and np.abs(out[0][2]).max() > 0
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
+def test_overlapped_count_is_the_same_system(cuda):
+    """solver_config['overlap_count']: row lengths, placement tables and row pointers on a side stream while the kernel
+    rows are built -- the system must be the serial one bit for bit (and stay so when the allocator recycles the side
+    stream's blocks over several solves)."""
+    import nksr_b200
+    xyz, nrm = clouds.sphere(40_000, noise=0.001)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    svh = nksr_b200.SparseFeatureHierarchy(0.02, 4, cuda).build_point_splatting(t(xyz))
+    osvh = O.OracleSVH(0.02, 4).build_from_keys([_np(k) for k in svh.keys])
+    feats = _feats(osvh, 4, 5)
+    nxyz = _np(torch.cat([svh.get_voxel_centers(d) for d in range(2)]))
+    nval = -(nxyz / np.linalg.norm(nxyz, axis=1, keepdims=True)).astype(np.float32)
+    pw, nw = 1e4 / xyz.shape[0], 1e4 / nxyz.shape[0] * 0.02 * 0.02
+    out = []
+    for overlap in (False, True, True, False, True):
+        field = _field(cuda, svh, feats, True)
+        field.solver_config.update(keep_system=True, max_iter=3, overlap_count=overlap)
+        field.solve(t(xyz), t(nxyz), t(nval), pw, nw, 1.0)
+        s_ = field.system
+        out.append([_np(a).copy() for a in (s_.rowptr, s_.col, s_.val, s_.rhs, s_.diag, field.alpha)])
+        del field
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("C,approx,mode", [(4, False, 0), (4, False, 1), (4, True, 1), (4, True, 2), (16, False, 1),
                                            (8, True, 2), (16, False, 0)])
 def test_voxel_rows_are_the_location_rows(cuda, C, approx, mode):

@@ -48,3 +48,24 @@ fi
 if has split1; then
   NKSR_BLOCK_SPLIT=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mesh > gpurun_out/${TAG}_bench_split1.json 2> gpurun_out/${TAG}_bench_split1.err
 fi
+if has w1; then
+  # r2w: the new kernels' own tests, then A/B bench lines of the interleaved row layout, the overlapped count and the U-Net
+  (time timeout 600 python -m pytest tests/test_gpu_network.py tests/test_gpu_parity.py -q --tb=short --timeout 240 -p no:cacheprovider 2>&1 | tail -60) > gpurun_out/${TAG}_pytest_new.log 2>&1
+  tail -3 gpurun_out/${TAG}_pytest_new.log
+  B="--steps 3 --warmup 3 --no-cpu-baseline --no-mesh"
+  timeout 300 python bench.py $B > gpurun_out/${TAG}_bench_base.json 2> gpurun_out/${TAG}_bench_base.err
+  NKSR_ROW_LAYOUT=interleaved timeout 300 python bench.py $B > gpurun_out/${TAG}_bench_ilv.json 2> gpurun_out/${TAG}_bench_ilv.err
+  NKSR_ROW_LAYOUT=interleaved NKSR_OVERLAP=1 timeout 300 python bench.py $B > gpurun_out/${TAG}_bench_ilv_overlap.json 2> gpurun_out/${TAG}_bench_ilv_overlap.err
+  NKSR_OVERLAP=1 timeout 300 python bench.py $B > gpurun_out/${TAG}_bench_overlap.json 2> gpurun_out/${TAG}_bench_overlap.err
+  timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-mesh --backbone unet-tf32 > gpurun_out/${TAG}_bench_unet_tf32.json 2> gpurun_out/${TAG}_bench_unet_tf32.err
+  timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-mesh --backbone unet > gpurun_out/${TAG}_bench_unet.json 2> gpurun_out/${TAG}_bench_unet.err
+  for f in base ilv ilv_overlap overlap unet_tf32 unet; do echo $f; python - <<PY
+import json
+try:
+    d=[json.loads(l) for l in open("gpurun_out/${TAG}_bench_$f.json") if l.startswith("{")][-1]
+    print(d["ms_per_step"], d["solve"]["stages_ms_timed_steps"], d.get("hbm_peak_allocated_gb"))
+except Exception as e:
+    print("no line:", e); print(open("gpurun_out/${TAG}_bench_$f.err").read()[-1500:])
+PY
+  done
+fi
