@@ -377,7 +377,7 @@ class KernelField(BaseField):
                     split = cand
                     break
         split = int(split)
-        if split < svh.depth and not cs.nrm_compact:
+        if split < svh.depth and cs.nrm_compact != 1:        # (compact gradient rows have no block kernel)
             nfl = call("nksr_gram_block_floats", svh.view(), split)
             if 0 < nfl * 4 <= max(budget, 0):
                 off = 0

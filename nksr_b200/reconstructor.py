@@ -183,14 +183,37 @@ def get_estimate_normal_preprocess_fn(knn: int = 64, max_angle_deg: float = 85.0
 
 
 class ChunkedField(BaseField):
-    """Union of independently reconstructed cubic chunks (reference semantics: serial chunk loop,
-    examples/recons_by_chunk.py:27-29).  A query is answered by the chunk whose core contains it."""
+    """Cubic chunks reconstructed one after the other (examples/recons_by_chunk.py:27-29, NKSR-USAGE.md:88-120).
 
-    def __init__(self, fields: List[KernelField], cores: torch.Tensor, chunk_size: float):
-        super().__init__(fields[0].svh)
+    Every chunk is solved on the points of its core cube plus a margin of two coarsest voxels.  With all chunks at
+    hand (`union_svh` given) the field is their partition-of-unity blend: the weight of chunk k is 1 in its core
+    shrunk by the margin, falls linearly to 0 at core + margin, and the weights are normalised -- so neighbouring
+    solutions cross-fade over the 2-margin band around a seam and `extract_dual_mesh` runs ONCE, on the hierarchy of the
+    whole cloud, over the blended field (a single welded mesh, no cracks along chunk faces).  Without it (a rank of the
+    multi-GPU chunk mapping holds only its own chunks) a query belongs to the chunk whose core contains it and the
+    chunk meshes are clipped to their cores and concatenated.
+
+    `chunk_tmp_device = cpu` (NKSR-USAGE.md:101,151): the solved chunk fields wait in host memory and visit
+    `compute_device` one at a time while they are evaluated -- this build has no CPU evaluator."""
+
+    def __init__(self, fields: List[KernelField], cores: torch.Tensor, chunk_size: float, margin: float = 0.0,
+                 union_svh=None, compute_device=None, adaptive_depth: int = 2):
+        super().__init__(union_svh if union_svh is not None else fields[0].svh)
         self.fields = fields
         self.cores = cores                       # (n_chunks, 3) integer chunk coordinates
         self.chunk_size = chunk_size
+        self.margin = float(margin)
+        self.blended = union_svh is not None and margin > 0
+        self.compute_device = torch.device(compute_device) if compute_device is not None else fields[0].svh.device
+        if self.blended:
+            self.set_mask_field(LayerField(union_svh, min(adaptive_depth, union_svh.depth)))
+
+    # a chunk field parked on the host visits the GPU for the duration of one evaluation
+    def _visit(self, f):
+        parked = f.svh.device.type != "cuda"
+        if parked:
+            f.to_(self.compute_device)
+        return parked
 
     def _owner(self, xyz):
         c = torch.floor(xyz / self.chunk_size).long()
@@ -199,24 +222,62 @@ class ChunkedField(BaseField):
             owner[(c == self.cores[k].to(xyz.device)[None]).all(dim=1)] = k
         return owner
 
+    def _weights(self, xyz, k):
+        """partition-of-unity weight of chunk k before normalisation: product over the axes of a ramp that is 0 at
+        core -+ margin and 1 from core +- margin inwards"""
+        lo = self.cores[k].to(xyz.device).float() * self.chunk_size - self.margin
+        hi = (self.cores[k].to(xyz.device).float() + 1.0) * self.chunk_size + self.margin
+        ramp = torch.minimum((xyz - lo[None]) / (2.0 * self.margin), (hi[None] - xyz) / (2.0 * self.margin))
+        return ramp.clamp(0.0, 1.0).prod(dim=1)
+
     def evaluate_f(self, xyz, grad=False):
-        owner = self._owner(xyz)
-        val = torch.zeros(xyz.shape[0], device=xyz.device)
-        g = torch.zeros((xyz.shape[0], 3), device=xyz.device) if grad else None
+        dev = xyz.device
+        val = torch.zeros(xyz.shape[0], device=dev)
+        g = torch.zeros((xyz.shape[0], 3), device=dev) if grad else None
+        if not self.blended:
+            owner = self._owner(xyz)
+        else:
+            wsum = torch.zeros(xyz.shape[0], device=dev)
         for k, f in enumerate(self.fields):
-            m = owner == k
-            if m.any():
-                r = f.evaluate_f(xyz[m].to(f.svh.device), grad=grad)
-                val[m] = r.value.to(xyz.device)
-                if grad:
-                    g[m] = r.gradient.to(xyz.device)
+            if self.blended:
+                w = self._weights(xyz, k)
+                m = w > 0
+            else:
+                m = owner == k
+            if not bool(m.any()):
+                continue
+            parked = self._visit(f)
+            r = f.evaluate_f(xyz[m].to(f.svh.device), grad=grad)
+            wk = w[m] if self.blended else 1.0
+            val[m] += wk * r.value.to(dev)
+            if grad:                              # (the gradient of the weights is left out: it vanishes off the seams)
+                g[m] += (wk[:, None] if self.blended else 1.0) * r.gradient.to(dev)
+            if self.blended:
+                wsum[m] += wk
+            if parked:
+                f.to_("cpu")
+        if self.blended:
+            inv = 1.0 / wsum.clamp(min=1e-12)
+            val = val * inv
+            if grad:
+                g = g * inv[:, None]
         return EvaluationResult(value=val, gradient=g)
 
+    def mask(self, xyz):
+        return self.mask_field.mask(xyz) if self.mask_field is not None else torch.ones(
+            xyz.shape[0], dtype=torch.bool, device=xyz.device)
+
     def extract_dual_mesh(self, grid_upsample: int = 1, mise_iter: int = 0, max_points: int = -1):
+        if self.blended:
+            from .meshing import extract_dual_mesh
+            return extract_dual_mesh(self, grid_upsample=grid_upsample, mise_iter=mise_iter, max_points=max_points)
         vs, fs, off = [], [], 0
-        dev = self.fields[0].svh.device
+        dev = self.compute_device
         for k, f in enumerate(self.fields):
+            parked = self._visit(f)
             m = f.extract_dual_mesh(grid_upsample=grid_upsample, mise_iter=mise_iter, max_points=max_points)
+            if parked:
+                f.to_("cpu")
             if m.f.shape[0] == 0:
                 continue
             cen = m.v[m.f].mean(dim=1)
@@ -235,6 +296,11 @@ class ChunkedField(BaseField):
     def to_(self, device):
         for f in self.fields:
             f.to_(device)
+        if torch.device(device).type == "cuda":
+            self.compute_device = torch.device(device)
+            if self.blended:
+                self.svh.to_(device)
+                self.mask_field.to_(device)
         return self
 
 
@@ -319,7 +385,7 @@ class Reconstructor:
         margin = voxel_size * (2 ** (self.tree_depth - 1)) * 2.0       # two coarsest voxels of overlap
         cidx = torch.floor(xyz / chunk_size).long()
         cores = torch.unique(cidx, dim=0)
-        fields, kept = [], []
+        fields, kept, core_pts = [], [], []
         for k in range(cores.shape[0]):
             if chunk_filter is not None and not chunk_filter(k, cores.shape[0]):
                 continue
@@ -335,10 +401,18 @@ class Reconstructor:
                 continue
             f = self._reconstruct_one(cx.contiguous(), cn, cs, voxel_size, approx_kernel_grad, solver_tol, fused_mode,
                                       solver_max_iter)
-            if self.chunk_tmp_device != self.device and self.chunk_tmp_device.type == "cuda":
-                f.to_(self.chunk_tmp_device)
+            if torch.device(self.chunk_tmp_device) != self.device:
+                f.to_(self.chunk_tmp_device)         # another GPU, or host memory (NKSR-USAGE.md:101)
             fields.append(f)
             kept.append(cores[k])
+            inner = (torch.floor(cx / chunk_size).long() == cores[k][None]).all(dim=1)
+            core_pts.append(cx[inner])
         if not fields:
             raise _lib.NksrError("no chunk contained enough points")
-        return ChunkedField(fields, torch.stack(kept), chunk_size)
+        union = None
+        if chunk_filter is None:
+            # all chunks are here: one hierarchy over the points the chunks kept, for the blended field's single mesh
+            union = SparseFeatureHierarchy(voxel_size, self.tree_depth, self.device).build_point_splatting(
+                torch.cat(core_pts).contiguous())
+        return ChunkedField(fields, torch.stack(kept), chunk_size, margin=margin, union_svh=union,
+                            compute_device=self.device, adaptive_depth=self.adaptive_depth)

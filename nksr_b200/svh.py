@@ -173,6 +173,9 @@ class SparseFeatureHierarchy:
 
     def view(self) -> _lib.SvhT:
         """C struct handed to the kernels (pointers stay valid while this object lives)."""
+        if torch.device(self.device).type != "cuda":
+            raise _lib.NksrError("this hierarchy is parked in host memory: move it back with to_(<cuda device>) "
+                                 "(nksr_b200 has no CPU path)")
         if self._view is None:
             v = _lib.SvhT()
             v.depth = self.depth
@@ -226,8 +229,8 @@ class SparseFeatureHierarchy:
 
     def to_(self, device):
         device = torch.device(device)
-        if device.type != "cuda":
-            raise _lib.NksrError("nksr_b200 hierarchies live on CUDA devices only")
+        # a CPU device only PARKS the tables in host memory (chunk_tmp_device = cpu, NKSR-USAGE.md:101): nothing can be
+        # computed there -- view() refuses until the hierarchy is moved back to a CUDA device
         self.device = device
         self.keys = [k.to(device) for k in self.keys]
         for name in ("parent", "child8", "nbr27"):

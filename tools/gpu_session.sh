@@ -69,3 +69,18 @@ except Exception as e:
 PY
   done
 fi
+if has w2; then
+  (time timeout 600 python -m pytest tests/test_gpu_parity.py -q --tb=short --timeout 240 -p no:cacheprovider -k "interleaved" 2>&1 | tail -30) > gpurun_out/${TAG}_pytest_ilv.log 2>&1
+  tail -3 gpurun_out/${TAG}_pytest_ilv.log
+  B="--steps 3 --warmup 3 --no-cpu-baseline --no-mesh"
+  NKSR_ROW_LAYOUT=interleaved timeout 300 python bench.py $B > gpurun_out/${TAG}_bench_ilv.json 2> gpurun_out/${TAG}_bench_ilv.err
+  python - <<PY
+import json
+d=[json.loads(l) for l in open("gpurun_out/${TAG}_bench_ilv.json") if l.startswith("{")][-1]
+print(d["ms_per_step"], d["solve"]["stages_ms_timed_steps"], d.get("hbm_peak_allocated_gb"))
+PY
+fi
+if has w3; then
+  (time timeout 600 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_parity.py tests/test_gpu_api_surface.py -q --tb=short --timeout 300 -p no:cacheprovider -k "chunk or reconstruct or distributed or api or surface" 2>&1 | tail -60) > gpurun_out/${TAG}_pytest_chunk.log 2>&1
+  tail -5 gpurun_out/${TAG}_pytest_chunk.log
+fi
