@@ -12,8 +12,9 @@
 // 128 sources are all absent is skipped (borders of the hierarchy).
 //   k_gather_gemm_f32 : fp32 FFMA, 8 x TN/16 outputs per thread (A tile transposed in smem: two LDS.128 + one LDS.128/64
 //                       per 32 / 16 FMAs) -- bit-for-bit an fp32 sum, the parity kernel
-//   k_gather_gemm_tf32: mma.sync.m16n8k8 TF32 (fp32 accumulate), one 16 x TN strip per warp -- the fast kernel; inputs are
-//                       rounded to TF32 (10-bit mantissa) with cvt.rna, so results differ from fp32 by ~1e-3 relative
+//   k_gather_gemm_tf32: mma.sync.m16n8k8 TF32 (fp32 accumulate), one 16 x TN strip per warp, operands staged by a
+//                       two-stage cp.async pipeline -- the fast kernel; inputs are rounded to TF32 (10-bit mantissa,
+//                       cvt.rna), so results differ from fp32 by ~1e-3 relative
 #include "common.cuh"
 
 namespace {
@@ -116,59 +117,111 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int TN>
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, const int src_bytes) {
+  // 16-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 fills the destination with zeros
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Two-stage pipeline: while the MMAs of one (offset k, 32-channel chunk) step run, the gathered rows and the weight
+// slice of the next step are already on their way into the other shared-memory buffer (cp.async, zero-fill for absent
+// sources).  The tile's 128 x K source indices are staged once (they are one contiguous block of `idx`), which also
+// tells which offsets have no source in the whole tile -- those steps are skipped.
+// WROUNDED: the weights were rounded to TF32 by the caller (no conversion of the B fragments here).
+template <int TN, bool WROUNDED>
 __global__ void __launch_bounds__(kThreads, 2)
 k_gather_gemm_tf32(const float* __restrict__ x, const int32_t* __restrict__ idx, int64_t n_out, int K,
                    const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ res,
                    float* __restrict__ y, int Cin, int Cout, int relu) {
-  constexpr int NT = TN / 8;                            // 8-column mma tiles per warp strip
-  __shared__ __align__(16) uint32_t As[kTM][kKC + 4];   // row-major, stride 36: fragment loads hit 32 distinct banks
-  __shared__ __align__(16) uint32_t Bs[kKC][TN + 8];    // stride = 8 mod 32: b0/b1 loads hit 32 distinct banks
+  constexpr int NT = TN / 8;                  // 8-column mma tiles per warp strip
+  constexpr int AS = kKC + 4;                 // A row stride (floats): fragment loads hit 32 distinct banks
+  constexpr int BS = TN + 8;                  // B row stride = 8 mod 32: b0 / b1 loads hit 32 distinct banks
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As = reinterpret_cast<float*>(smem_raw);                    // [2][kTM][AS]
+  float* Bs = As + 2 * kTM * AS;                                     // [2][kKC][BS]
+  int32_t* src_s = reinterpret_cast<int32_t*>(Bs + 2 * kKC * BS);    // [kTM][K]
+  __shared__ unsigned kmask;                                         // bit k: some row of the tile has a source at k
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int64_t row0 = (int64_t)blockIdx.x * kTM;
   const int n0 = blockIdx.y * TN;
+  const int rows_here = (int)min((int64_t)kTM, n_out - row0);
+  if (tid == 0) kmask = 0u;
+  __syncthreads();
+  {
+    unsigned mine = 0u;
+    const int32_t* ip = idx + row0 * K;
+    for (int e = tid; e < kTM * K; e += kThreads) {
+      const int r = e / K;
+      const int v = r < rows_here ? __ldg(ip + e) : -1;
+      src_s[e] = v;
+      if (v >= 0) mine |= 1u << (e - r * K);
+    }
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicOr(&kmask, mine);
+  }
+  __syncthreads();
+  const unsigned km = kmask;
+  const int nchunk = Cin / kKC;
+  const int nsteps = __popc(km) * nchunk;
+
   float acc[NT][4];
 #pragma unroll
   for (int j = 0; j < NT; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 
-  for (int k = 0; k < K; ++k) {
-    int src_l = -1;
-    if (lane < 16) {
-      const int64_t r = row0 + wid * 16 + lane;
-      if (r < n_out) src_l = __ldg(idx + r * K + k);
-    }
-    if (!__syncthreads_or(src_l >= 0)) continue;
-    for (int c0 = 0; c0 < Cin; c0 += kKC) {
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        const int s = __shfl_sync(0xffffffffu, src_l, j);
-        As[wid * 16 + j][lane] = s >= 0 ? to_tf32(__ldg(x + (int64_t)s * Cin + c0 + lane)) : 0u;
-      }
-      const float* wp = W + ((int64_t)k * Cin + c0) * Cout + n0;
-      for (int e = tid; e < kKC * TN / 4; e += kThreads) {
-        const int r = e / (TN / 4), q = e % (TN / 4);
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)r * Cout) + q);
-        uint4 u;
-        u.x = to_tf32(w4.x); u.y = to_tf32(w4.y); u.z = to_tf32(w4.z); u.w = to_tf32(w4.w);
-        *reinterpret_cast<uint4*>(&Bs[r][q * 4]) = u;
-      }
-      __syncthreads();
-      const uint32_t(*Aw)[kKC + 4] = As + wid * 16;     // this warp's 16 rows
+  // step s -> (k = the (s / nchunk)-th set bit of km, c0 = (s % nchunk) * 32)
+  auto issue = [&](const int s, const int buf) {
+    const int k = __fns(km, 0, s / nchunk + 1);
+    const int c0 = (s - (s / nchunk) * nchunk) * kKC;
+    float* a = As + buf * kTM * AS;
 #pragma unroll
-      for (int ks = 0; ks < kKC; ks += 8) {
-        uint32_t a[4];
-        a[0] = Aw[g][ks + t];
-        a[1] = Aw[g + 8][ks + t];
-        a[2] = Aw[g][ks + t + 4];
-        a[3] = Aw[g + 8][ks + t + 4];
-#pragma unroll
-        for (int j = 0; j < NT; ++j) mma_tf32(acc[j], a, Bs[ks + t][j * 8 + g], Bs[ks + t + 4][j * 8 + g]);
-      }
-      __syncthreads();
+    for (int j = 0; j < kTM * 8 / kThreads; ++j) {
+      const int e = tid + j * kThreads;
+      const int r = e >> 3, seg = e & 7;
+      const int sidx = src_s[r * K + k];
+      const float* gp = x + (int64_t)(sidx >= 0 ? sidx : 0) * Cin + c0 + seg * 4;
+      cp_async16(a + r * AS + seg * 4, gp, sidx >= 0 ? 16 : 0);
     }
+    float* b = Bs + buf * kKC * BS;
+    const float* wp = W + ((int64_t)k * Cin + c0) * Cout + n0;
+    for (int e = tid; e < kKC * TN / 4; e += kThreads) {
+      const int r = e / (TN / 4), q = e % (TN / 4);
+      cp_async16(b + r * BS + q * 4, wp + (int64_t)r * Cout + q * 4, 16);
+    }
+    cp_async_commit();
+  };
+
+  if (nsteps > 0) issue(0, 0);
+  for (int s = 0; s < nsteps; ++s) {
+    const int buf = s & 1;
+    if (s + 1 < nsteps) {
+      issue(s + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* Aw = As + buf * kTM * AS + wid * 16 * AS;      // this warp's 16 rows
+    const float* Bb = Bs + buf * kKC * BS;
+#pragma unroll
+    for (int ks = 0; ks < kKC; ks += 8) {
+      uint32_t a[4];
+      a[0] = to_tf32(Aw[g * AS + ks + t]);
+      a[1] = to_tf32(Aw[(g + 8) * AS + ks + t]);
+      a[2] = to_tf32(Aw[g * AS + ks + t + 4]);
+      a[3] = to_tf32(Aw[(g + 8) * AS + ks + t + 4]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float b0 = Bb[(ks + t) * BS + j * 8 + g], b1 = Bb[(ks + t + 4) * BS + j * 8 + g];
+        mma_tf32(acc[j], a, WROUNDED ? __float_as_uint(b0) : to_tf32(b0), WROUNDED ? __float_as_uint(b1) : to_tf32(b1));
+      }
+    }
+    __syncthreads();                                            // the buffer is refilled two steps ahead
   }
   // epilogue: rows g / g+8 of the warp's strip, columns 2t / 2t+1 of every 8-column tile
 #pragma unroll
@@ -190,6 +243,23 @@ k_gather_gemm_tf32(const float* __restrict__ x, const int32_t* __restrict__ idx,
   }
 }
 
+template <int TN>
+size_t tf32_smem_bytes(int K) {
+  return (size_t)(2 * kTM * (kKC + 4) + 2 * kKC * (TN + 8)) * sizeof(float) + (size_t)kTM * K * sizeof(int32_t);
+}
+
+template <int TN, bool WROUNDED>
+int launch_tf32(dim3 grid, cudaStream_t s, const float* x, const int32_t* idx, int64_t n_out, int K, const float* W,
+                const float* bias, const float* res, float* y, int c_in, int c_out, int relu) {
+  const size_t smem = tf32_smem_bytes<TN>(K);
+  if (smem > 200 * 1024) return NKSR_E_INVALID;
+  if (cudaFuncSetAttribute(k_gather_gemm_tf32<TN, WROUNDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return NKSR_E_CUDA;
+  k_gather_gemm_tf32<TN, WROUNDED><<<grid, kThreads, smem, s>>>(x, idx, n_out, K, W, bias, res, y, c_in, c_out, relu);
+  return NKSR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -202,13 +272,22 @@ int nksr_gather_gemm(const float* x, const int32_t* idx, int64_t n_out, int K, c
   cudaStream_t s = as_stream(stream);
   const int tn = c_out % 64 == 0 ? 64 : 32;
   const dim3 grid((unsigned)((n_out + kTM - 1) / kTM), (unsigned)(c_out / tn));
-#define NKSR_GG(KERNEL, TN) KERNEL<TN><<<grid, kThreads, 0, s>>>(x, idx, n_out, K, W, bias, res, y, c_in, c_out, relu)
+  if (K > 32 && tf32) return NKSR_E_INVALID;           // the tile's offset mask is one 32-bit word
   if (tf32) {
-    if (tn == 64) NKSR_GG(k_gather_gemm_tf32, 64); else NKSR_GG(k_gather_gemm_tf32, 32);
+    int rc;
+    if (tn == 64)
+      rc = tf32 == 2 ? launch_tf32<64, true>(grid, s, x, idx, n_out, K, W, bias, res, y, c_in, c_out, relu)
+                     : launch_tf32<64, false>(grid, s, x, idx, n_out, K, W, bias, res, y, c_in, c_out, relu);
+    else
+      rc = tf32 == 2 ? launch_tf32<32, true>(grid, s, x, idx, n_out, K, W, bias, res, y, c_in, c_out, relu)
+                     : launch_tf32<32, false>(grid, s, x, idx, n_out, K, W, bias, res, y, c_in, c_out, relu);
+    if (rc != NKSR_OK) return rc;
   } else {
-    if (tn == 64) NKSR_GG(k_gather_gemm_f32, 64); else NKSR_GG(k_gather_gemm_f32, 32);
+    if (tn == 64)
+      k_gather_gemm_f32<64><<<grid, kThreads, 0, s>>>(x, idx, n_out, K, W, bias, res, y, c_in, c_out, relu);
+    else
+      k_gather_gemm_f32<32><<<grid, kThreads, 0, s>>>(x, idx, n_out, K, W, bias, res, y, c_in, c_out, relu);
   }
-#undef NKSR_GG
   NKSR_CHECK_LAUNCH();
   return NKSR_OK;
 }

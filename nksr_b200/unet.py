@@ -27,8 +27,14 @@ from torch import nn
 from ._lib import call, stream_ptr
 
 
+def round_tf32(w: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32 value (10-bit mantissa, ties away from zero: what cvt.rna.tf32.f32 does), kept as fp32"""
+    return ((w.contiguous().view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+
+
 def gather_gemm(x, idx, weight, bias=None, res=None, relu=False, tf32=False, impl="cuda"):
-    """y[i] = act(bias + res[i] + sum_k x[idx[i, k]] @ weight[k]) over the valid (>= 0) entries of idx (n_out, K)."""
+    """y[i] = act(bias + res[i] + sum_k x[idx[i, k]] @ weight[k]) over the valid (>= 0) entries of idx (n_out, K).
+    tf32: False / 0 = fp32 FFMA kernel; True / 1 = TF32 tensor-core kernel; 2 = the same, `weight` already TF32-rounded."""
     n_out, K = idx.shape
     c_in, c_out = weight.shape[1], weight.shape[2]
     assert weight.shape[0] == K and x.shape[1] == c_in
@@ -49,7 +55,7 @@ def gather_gemm(x, idx, weight, bias=None, res=None, relu=False, tf32=False, imp
     w = weight.contiguous()
     y = torch.empty((n_out, c_out), dtype=torch.float32, device=x.device)
     call("nksr_gather_gemm", x, idx, n_out, K, w, bias.contiguous() if bias is not None else None,
-         res.contiguous() if res is not None else None, y, c_in, c_out, int(bool(relu)), int(bool(tf32)),
+         res.contiguous() if res is not None else None, y, c_in, c_out, int(bool(relu)), int(tf32),
          stream_ptr(x.device))
     return y
 
@@ -65,6 +71,8 @@ class SparseConv(nn.Module):
         nn.init.uniform_(self.weight, -bound, bound)
 
     def forward(self, x, idx, res=None, relu=True, tf32=False, impl="cuda"):
+        if tf32 and impl == "cuda":              # weights rounded once here, not per fragment in the kernel
+            return gather_gemm(x, idx, round_tf32(self.weight.detach()), self.bias, res, relu, 2, impl)
         return gather_gemm(x, idx, self.weight, self.bias, res, relu, tf32, impl)
 
 

@@ -182,14 +182,17 @@ def test_chunked_reconstruction_blends_and_welds(cuda):
     mc = field.extract_dual_mesh(mise_iter=1)
     field.blended = True
     assert _boundary(_np(mc.v), _np(mc.f))[0].sum() > blen.sum() + 20.0
-    # continuity across the seam x = 0: field values on both sides of the plane, 1e-4 apart
+    # continuity across the seam x = 0 (also a voxel face, where any single field may jump if a containing voxel is
+    # inactive on one side): values 1e-4 apart on both sides of the plane jump no more than the un-chunked field's
     rng = np.random.default_rng(0)
-    q = (xyz[rng.integers(0, xyz.shape[0], 4000)] * rng.uniform(0.97, 1.03, (4000, 1))).astype(np.float32)
+    q = (xyz[rng.integers(0, xyz.shape[0], 4000)] * rng.uniform(0.995, 1.005, (4000, 1))).astype(np.float32)
     qa, qb = q.copy(), q.copy()
     qa[:, 0], qb[:, 0] = -5e-5, 5e-5
     fa, fb = field.evaluate_f(t(qa)).value, field.evaluate_f(t(qb)).value
-    scale = float(field.evaluate_f(t(q * 1.05)).value.abs().median())
-    assert float((fa - fb).abs().max()) < 0.02 * max(scale, 1e-6)
+    wa, wb = whole.evaluate_f(t(qa)).value, whole.evaluate_f(t(qb)).value
+    scale = float(whole.evaluate_f(t(q * 1.03)).value.abs().median())
+    assert float((fa - fb).abs().max()) <= float((wa - wb).abs().max()) + 0.02 * max(scale, 1e-6)
+    assert float((fa - wa).abs().median()) < 0.05 * max(scale, 1e-6)          # and the blend is the same function there
     # chunk_tmp_device = cpu: the solved chunks wait in host memory, visit the GPU per evaluation, return to the host
     rec.chunk_tmp_device = torch.device("cpu")
     parked = rec.reconstruct(t(xyz), t(nrm), detail_level=None, chunk_size=4.0, solver_tol=1e-5)

@@ -84,3 +84,16 @@ if has w3; then
   (time timeout 600 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_parity.py tests/test_gpu_api_surface.py -q --tb=short --timeout 300 -p no:cacheprovider -k "chunk or reconstruct or distributed or api or surface" 2>&1 | tail -60) > gpurun_out/${TAG}_pytest_chunk.log 2>&1
   tail -5 gpurun_out/${TAG}_pytest_chunk.log
 fi
+if has w4; then
+  (time timeout 600 python -m pytest tests/test_gpu_network.py tests/test_gpu_pipeline.py -q --tb=short --timeout 300 -p no:cacheprovider -k "gather or unet or chunk" 2>&1 | tail -60) > gpurun_out/${TAG}_pytest_w4.log 2>&1
+  tail -5 gpurun_out/${TAG}_pytest_w4.log
+  timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-mesh --backbone unet-tf32 > gpurun_out/${TAG}_bench_unet_tf32.json 2> gpurun_out/${TAG}_bench_unet_tf32.err
+  python - <<PY
+import json
+try:
+    d=[json.loads(l) for l in open("gpurun_out/${TAG}_bench_unet_tf32.json") if l.startswith("{")][-1]
+    print(d["ms_per_step"], d["solve"]["stages_ms_timed_steps"])
+except Exception as e:
+    print("no line", e); print(open("gpurun_out/${TAG}_bench_unet_tf32.err").read()[-1500:])
+PY
+fi
