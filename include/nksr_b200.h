@@ -103,7 +103,9 @@ NKSR_API int nksr_pool_children(const int32_t* child8, const float* in, int64_t 
  * idx = nbr27[l] (K = 27): 3x3x3 convolution on level l; idx = child8[l+1] (K = 8): stride-2 convolution l -> l+1.
  * c_in and c_out multiples of 32; bias / res may be NULL; relu: 0/1; tf32: 0 = fp32 FFMA, 1 = mma.sync TF32 (fp32
  * accumulation, operands rounded to TF32 in the kernel, K <= 32), 2 = the same with W already rounded to TF32 by the
- * caller (low 13 mantissa bits zero) */
+ * caller (low 13 mantissa bits zero), 3 = tcgen05.mma kind::tf32 with the accumulator in TMEM (K <= 32 x 32-channel
+ * steps staged in SWIZZLE_128B shared memory by cp.async; W rounded to TF32 by the caller AND transposed to
+ * K x c_out x c_in, the tensor core's K-major operand order) */
 NKSR_API int nksr_gather_gemm(const float* x, const int32_t* idx, int64_t n_out, int K, const float* W,
                      const float* bias, const float* res, float* y, int c_in, int c_out, int relu, int tf32,
                      void* stream);

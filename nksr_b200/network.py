@@ -73,7 +73,8 @@ class NKSRNetwork(nn.Module):
         self.backbone = str(hp["backbone"])
         if self.backbone not in ("pool", "unet"):
             raise ValueError("backbone: 'pool' or 'unet'")
-        self.tf32 = str(hp["precision"]) == "tf32"
+        # precision: 'fp32' (FFMA kernel), 'tf32' (mma.sync), 'tc' (tcgen05 + TMEM) -- csrc/sparse_conv.cu
+        self.tf32 = {"tf32": True, "tc": 3}.get(str(hp["precision"]), False)
         interp = hp["interpolator"]
         gen = torch.Generator().manual_seed(int(hp["seed"]))
         state = torch.random.get_rng_state()

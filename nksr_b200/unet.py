@@ -34,9 +34,13 @@ def round_tf32(w: torch.Tensor) -> torch.Tensor:
 
 def gather_gemm(x, idx, weight, bias=None, res=None, relu=False, tf32=False, impl="cuda"):
     """y[i] = act(bias + res[i] + sum_k x[idx[i, k]] @ weight[k]) over the valid (>= 0) entries of idx (n_out, K).
-    tf32: False / 0 = fp32 FFMA kernel; True / 1 = TF32 tensor-core kernel; 2 = the same, `weight` already TF32-rounded."""
+    tf32: False / 0 = fp32 FFMA kernel; True / 1 = TF32 mma.sync kernel; 2 = the same, `weight` already TF32-rounded;
+    3 = the tcgen05 kernel (TMEM accumulator), `weight` already TF32-rounded and transposed to (K, c_out, c_in)."""
     n_out, K = idx.shape
-    c_in, c_out = weight.shape[1], weight.shape[2]
+    if int(tf32) == 3 and impl == "cuda":
+        c_out, c_in = weight.shape[1], weight.shape[2]
+    else:
+        c_in, c_out = weight.shape[1], weight.shape[2]
     assert weight.shape[0] == K and x.shape[1] == c_in
     if impl == "torch":
         y = torch.zeros((n_out, c_out), dtype=torch.float32, device=x.device)
@@ -71,6 +75,12 @@ class SparseConv(nn.Module):
         nn.init.uniform_(self.weight, -bound, bound)
 
     def forward(self, x, idx, res=None, relu=True, tf32=False, impl="cuda"):
+        if int(tf32) == 3 and impl == "cuda":    # tcgen05: rounded AND transposed to the MMA's K-major operand order
+            key = (self.weight._version, self.weight.data_ptr())
+            if getattr(self, "_tc_key", None) != key:
+                self._tc_key = key
+                self._tc_weight = round_tf32(self.weight.detach()).transpose(1, 2).contiguous()
+            return gather_gemm(x, idx, self._tc_weight, self.bias, res, relu, 3, impl)
         if tf32 and impl == "cuda":              # weights rounded once here, not per fragment in the kernel
             return gather_gemm(x, idx, round_tf32(self.weight.detach()), self.bias, res, relu, 2, impl)
         return gather_gemm(x, idx, self.weight, self.bias, res, relu, tf32, impl)

@@ -76,6 +76,36 @@ def test_gather_gemm_edge_cases(cuda, tf32):
         gather_gemm(x[:, :16].contiguous(), idx, w[:, :16].contiguous(), None, None, False, tf32=tf32)
 
 
+@pytest.mark.parametrize("taps,c_in,c_out", [(27, 32, 32), (27, 64, 32), (27, 32, 64), (27, 128, 64), (8, 32, 64),
+                                             (27, 32, 96), (27, 256, 256)])
+def test_gather_gemm_tcgen05_matches_torch(cuda, taps, c_in, c_out):
+    """the tcgen05 / TMEM kernel (tf32 = 3: operands read as TF32 by the tensor core, fp32 accumulation in TMEM) against
+    dense torch fp32, the same bound as the mma.sync TF32 kernel; also bitwise repeatable (one accumulation order)"""
+    from nksr_b200.unet import gather_gemm, round_tf32
+    svh, _ = _svh(cuda)
+    g = torch.Generator(device="cpu").manual_seed(taps * 1000 + c_in + c_out)
+    idx, n_in = (svh.nbr27[0], svh.num_voxels(0)) if taps == 27 else (svh.child8[1], svh.num_voxels(0))
+    n_out = idx.shape[0]
+    x = torch.randn((n_in, c_in), generator=g).to(cuda)
+    w = (torch.randn((taps, c_in, c_out), generator=g) / (taps * c_in) ** 0.5).to(cuda)
+    wt = round_tf32(w).transpose(1, 2).contiguous()
+    b = torch.randn(c_out, generator=g).to(cuda)
+    res = torch.randn((n_out, c_out), generator=g).to(cuda)
+    for bias, r, relu in [(b, res, True), (None, None, False), (b, None, False)]:
+        ref = gather_gemm(x, idx, w, bias, r, relu, impl="torch")
+        out = gather_gemm(x, idx, wt, bias, r, relu, tf32=3)
+        assert out.shape == ref.shape and torch.isfinite(out).all()
+        assert _close(out, ref, 4e-3), float((out - ref).abs().max())
+    assert torch.equal(gather_gemm(x, idx, wt, b, res, True, tf32=3), gather_gemm(x, idx, wt, b, res, True, tf32=3))
+    # edge cases: no source at all, one row with one source, an empty output
+    none = torch.full((300, taps), -1, dtype=torch.int32, device=cuda)
+    assert torch.equal(gather_gemm(x, none, wt, b, res[:300], True, tf32=3), torch.relu(b + res[:300]))
+    one = torch.full((1, taps), -1, dtype=torch.int32, device=cuda)
+    one[0, taps // 2] = 7
+    assert _close(gather_gemm(x, one, wt, None, None, False, tf32=3), x[7:8] @ w[taps // 2], 4e-3)
+    assert gather_gemm(x, none[:0], wt, b, None, True, tf32=3).shape == (0, c_out)
+
+
 def test_unet_forward_matches_torch_reference(cuda):
     """the whole backbone (point encoder -> residual sparse-conv U-Net -> heads) with the CUDA convolution against the
     same modules with the dense-gather torch convolution; then TF32 against fp32"""
@@ -99,6 +129,24 @@ def test_unet_forward_matches_torch_reference(cuda):
             assert torch.isfinite(a).all() and float(b.abs().max()) > 0
             assert _close(a, b, 1e-4), (name, l, float((a - b).abs().max()), float(b.abs().max()))
             assert _close(c, b, 2e-2), (name, l, float((c - b).abs().max()), float(b.abs().max()))
+
+
+def test_unet_forward_tcgen05_matches_torch_reference(cuda):
+    """the whole backbone with every convolution on the tcgen05 kernel (precision='tc') against the torch fp32 modules"""
+    from nksr_b200.network import NKSRNetwork
+    svh, xyz = _svh(cuda, n=20_000, depth=3)
+    net = NKSRNetwork(dict(backbone="unet", tree_depth=3, kernel_dim=4, precision="tc")).to(cuda)
+    assert net.tf32 == 3
+    g = torch.Generator(device="cpu").manual_seed(5)
+    feat = torch.nn.functional.normalize(torch.randn((xyz.shape[0], 3), generator=g), dim=1).to(cuda)
+    with torch.no_grad():
+        enc = net.encoder(xyz, feat, svh, 0)
+        ref = net.backbone_net(enc.x0, svh, impl="torch")
+        tc = net.backbone_net(enc.x0, svh, tf32=3)
+    for l in range(3):
+        for name in ("structure", "normal", "basis", "udf", "decoder"):
+            a, b = getattr(tc, name)[l], getattr(ref, name)[l]
+            assert torch.isfinite(a).all() and _close(a, b, 2e-2), (name, l, float((a - b).abs().max()))
 
 
 def test_unet_backbone_through_the_reconstructor(cuda):

@@ -97,3 +97,24 @@ except Exception as e:
     print("no line", e); print(open("gpurun_out/${TAG}_bench_unet_tf32.err").read()[-1500:])
 PY
 fi
+if has y1; then
+  # r2y: tcgen05 gather-GEMM diagnostics first (own process: a trap there must not take the suite down), then the
+  # whole -m gpu suite without the tcgen05 tests, smoke, the tcgen05 tests, the headline bench, the U-Net bench on tcgen05
+  timeout 240 python tools/tc_diag.py ${TAG} > gpurun_out/${TAG}_tc_diag.log 2>&1; echo "tc_diag rc=$?"; tail -5 gpurun_out/${TAG}_tc_diag.log | cut -c1-400
+  (time timeout 600 python -m pytest tests -m gpu -q --tb=short --timeout 240 -p no:cacheprovider -k "not tcgen05" 2>&1 | tail -40) > gpurun_out/${TAG}_pytest.log 2>&1
+  tail -4 gpurun_out/${TAG}_pytest.log
+  timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; tail -1 gpurun_out/${TAG}_smoke.log
+  (timeout 300 python -m pytest tests/test_gpu_network.py -m gpu -q --tb=short --timeout 120 -p no:cacheprovider -k "tcgen05" 2>&1 | tail -40) > gpurun_out/${TAG}_pytest_tcgen05.log 2>&1
+  tail -3 gpurun_out/${TAG}_pytest_tcgen05.log
+  timeout 400 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+  tail -c 700 gpurun_out/${TAG}_bench.json
+  timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-mesh --backbone unet-tc > gpurun_out/${TAG}_bench_unet_tc.json 2> gpurun_out/${TAG}_bench_unet_tc.err
+  python - <<PY
+import json
+try:
+    d=[json.loads(l) for l in open("gpurun_out/${TAG}_bench_unet_tc.json") if l.startswith("{")][-1]
+    print("unet-tc", d["ms_per_step"], d["solve"]["stages_ms_timed_steps"])
+except Exception as e:
+    print("no unet-tc line", e); print(open("gpurun_out/${TAG}_bench_unet_tc.err").read()[-800:])
+PY
+fi
