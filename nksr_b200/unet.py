@@ -10,8 +10,10 @@ pretrained checkpoint is a network download (models/nksr_net.py:36-38).
 
 Where the time goes is the 3x3x3 sparse convolution, and that is a hand-written kernel (csrc/sparse_conv.cu,
 `nksr_gather_gemm`): a gather-GEMM over the index tables the hierarchy already holds (nbr27 for the 3^3 stencil,
-child8 for the stride-2 convolution), fp32 FFMA or TF32 mma.sync.  Point-wise MLPs, the per-octant up-projection and
-the heads are dense library GEMMs (torch), as BASELINE.json's north_star keeps the network on PyTorch.
+child8 for the stride-2 convolution, a parent-by-octant table for the up-projection), fp32 FFMA, TF32 mma.sync, or TF32
+tcgen05.mma with the accumulator in TMEM (`precision='tc'`).  The skip concatenation is never materialised (the decoder
+convolution runs over its two inputs in turn).  Point-wise MLPs and the heads are dense library GEMMs (torch), as
+BASELINE.json's north_star keeps the network on PyTorch.
 
 Every module has `impl='torch'`: the same arithmetic in plain torch (dense gathers) -- the fp32 reference the GPU
 tests compare the kernel with (tests/test_gpu_network.py).
@@ -64,8 +66,38 @@ def gather_gemm(x, idx, weight, bias=None, res=None, relu=False, tf32=False, imp
     return y
 
 
+def kernel_weights(cache, name, weight, mode, splits=None):
+    """`weight` (K, c_in, c_out) in the form the kernel of `mode` takes, cut along c_in into `splits` parts (the inputs of
+    a convolution over a channel concatenation): mode 0 as is; 1 / 2 rounded to TF32; 3 rounded and transposed to
+    (K, c_out, c_in).  Cached in `cache[name]` until the parameter is modified or moved."""
+    key = (int(mode), splits, weight._version, weight.data_ptr())
+    hit = cache.get(name)
+    if hit is None or hit[0] != key:
+        w = weight.detach()
+        if mode:
+            w = round_tf32(w)
+        parts = [w] if splits is None else list(torch.split(w, list(splits), dim=1))
+        parts = [(q.transpose(1, 2) if int(mode) == 3 else q).contiguous() for q in parts]
+        cache[name] = (key, parts)
+    return cache[name][1]
+
+
+_KERNEL_FLAG = {0: 0, 1: 2, 2: 2, 3: 3}          # the weights are always rounded on the host (flag 2), never per fragment
+
+
+def conv_parts(parts, idx, weights, bias, res, relu, mode):
+    """y = act(bias + res + sum_p conv(parts[p], weights[p])): the convolution of the channel concatenation of `parts`
+    without materialising it -- one kernel call per part, each adding to the previous one's output"""
+    y = res
+    for i, (x, w) in enumerate(zip(parts, weights)):
+        last = i == len(parts) - 1
+        y = gather_gemm(x, idx, w, bias if last else None, y, relu and last, _KERNEL_FLAG[int(mode)])
+    return y
+
+
 class SparseConv(nn.Module):
-    """K-tap sparse convolution: weight (K, c_in, c_out) + bias; the taps' sources come from an index table."""
+    """K-tap sparse convolution: weight (K, c_in, c_out) + bias; the taps' sources come from an index table.  `x` may be
+    a tuple of tensors: the convolution then runs over their channel concatenation (the U-Net's skip connections)."""
 
     def __init__(self, taps, c_in, c_out):
         super().__init__()
@@ -73,17 +105,17 @@ class SparseConv(nn.Module):
         self.bias = nn.Parameter(torch.zeros(c_out))
         bound = math.sqrt(6.0 / (taps * c_in))                       # He-uniform over the full stencil
         nn.init.uniform_(self.weight, -bound, bound)
+        self._wcache = {}
 
     def forward(self, x, idx, res=None, relu=True, tf32=False, impl="cuda"):
-        if int(tf32) == 3 and impl == "cuda":    # tcgen05: rounded AND transposed to the MMA's K-major operand order
-            key = (self.weight._version, self.weight.data_ptr())
-            if getattr(self, "_tc_key", None) != key:
-                self._tc_key = key
-                self._tc_weight = round_tf32(self.weight.detach()).transpose(1, 2).contiguous()
-            return gather_gemm(x, idx, self._tc_weight, self.bias, res, relu, 3, impl)
-        if tf32 and impl == "cuda":              # weights rounded once here, not per fragment in the kernel
-            return gather_gemm(x, idx, round_tf32(self.weight.detach()), self.bias, res, relu, 2, impl)
-        return gather_gemm(x, idx, self.weight, self.bias, res, relu, tf32, impl)
+        parts = tuple(x) if isinstance(x, (tuple, list)) else (x,)
+        if impl != "cuda":
+            xc = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+            return gather_gemm(xc, idx, self.weight, self.bias, res, relu, False, impl)
+        mode = int(tf32)
+        splits = tuple(int(q.shape[1]) for q in parts) if len(parts) > 1 else None
+        ws = kernel_weights(self._wcache, "w", self.weight, mode, splits)
+        return conv_parts(parts, idx, ws, self.bias, res, relu, mode)
 
 
 class PointEncoder(nn.Module):
@@ -127,6 +159,24 @@ def octant_of_children(child8, n_children):
     return octant
 
 
+def up_table(svh, l):
+    """(n_l, 8) int32 gather table of the up-projection l+1 -> l: row i holds its parent's index in the column of its
+    octant and -1 elsewhere.  Built once per hierarchy level (cached on the hierarchy object, keyed by the tables it was
+    derived from)."""
+    child8, parent = svh.child8[l + 1], svh.parent[l]
+    cache = svh.__dict__.setdefault("_unet_up_tables", {})
+    key = (child8.data_ptr(), parent.data_ptr(), str(parent.device))
+    hit = cache.get(l)
+    if hit is None or hit[0] != key:
+        n_l = svh.num_voxels(l)
+        octant = octant_of_children(child8, n_l)
+        rows = torch.nonzero((octant >= 0) & (parent >= 0)).squeeze(1)
+        idx = torch.full((n_l, 8), -1, dtype=torch.int32, device=parent.device)
+        idx[rows, octant[rows]] = parent[rows].to(torch.int32)
+        cache[l] = (key, idx)
+    return cache[l][1]
+
+
 class SparseUNet(nn.Module):
     """Residual sparse-conv U-Net over the levels of a SparseFeatureHierarchy (level 0 = finest):
        down path  l = 0..D-1:  x_l = ResBlock_l(x_l)  (two 3^3 convs);  x_{l+1} = relu(stride-2 conv of x_l)
@@ -147,9 +197,15 @@ class SparseUNet(nn.Module):
             nn.init.uniform_(p, -math.sqrt(6.0 / p.shape[1]), math.sqrt(6.0 / p.shape[1]))
         self.dec = nn.ModuleList([SparseConv(27, 2 * ch[l], ch[l]) for l in range(depth - 1)])
         self.heads = nn.ModuleList([nn.Linear(ch[l], 6 + 2 * kernel_dim) for l in range(depth)])
+        self._wcache = {}
 
-    def up_project(self, y_coarse, svh, l):
-        """level l+1 -> level l: every child takes its parent's features through the weight of its octant"""
+    def up_project(self, y_coarse, svh, l, tf32=False, impl="cuda"):
+        """level l+1 -> level l: every child takes its parent's features through the weight of its octant.  On the GPU
+        this is the gather-GEMM kernel again, 8 taps with one valid source per row (`up_table`); impl='torch' is the
+        plain per-octant loop the tests compare it with."""
+        if impl == "cuda":
+            ws = kernel_weights(self._wcache, f"up{l}", self.up[l], int(tf32))
+            return conv_parts((y_coarse,), up_table(svh, l), ws, None, None, False, int(tf32))
         n_l = svh.num_voxels(l)
         out = torch.zeros((n_l, self.channels[l]), device=y_coarse.device)
         octant = octant_of_children(svh.child8[l + 1], n_l)
@@ -175,8 +231,8 @@ class SparseUNet(nn.Module):
         y = xs[D - 1]
         ys[D - 1] = y
         for l in range(D - 2, -1, -1):
-            u = self.up_project(y, svh, l)
-            y = self.dec[l](torch.cat([xs[l], u], dim=1), svh.nbr27[l], relu=True, **kw)
+            u = self.up_project(y, svh, l, **kw)
+            y = self.dec[l]((xs[l], u), svh.nbr27[l], relu=True, **kw)         # conv over [skip ; up], not concatenated
             ys[l] = y
         C = self.kernel_dim
         out = SimpleNamespace(structure={}, normal={}, basis={}, udf={}, decoder={})

@@ -182,21 +182,33 @@ def test_chunked_reconstruction_blends_and_welds(cuda):
     mc = field.extract_dual_mesh(mise_iter=1)
     field.blended = True
     assert _boundary(_np(mc.v), _np(mc.f))[0].sum() > blen.sum() + 20.0
-    # continuity across the seam x = 0 (also a voxel face, where any single field may jump if a containing voxel is
-    # inactive on one side): values 1e-4 apart on both sides of the plane jump no more than the un-chunked field's
+    # continuity across the seam x = 0.  The plane is also a voxel face, where ANY single field may jump (a containing
+    # voxel active on one side only -- the un-chunked field does too), so the property of the blend is pointwise: with
+    # continuous weights, f(a) - f(b) = sum_k w_k(a) (f_k(a) - f_k(b)) + O(|a - b|): for two points 1e-4 apart on the two
+    # sides of the seam the blend jumps no more than the largest jump among the chunk fields it blends there (an
+    # owner-takes-all union jumps by f_A - f_B instead)
     rng = np.random.default_rng(0)
     q = (xyz[rng.integers(0, xyz.shape[0], 4000)] * rng.uniform(0.995, 1.005, (4000, 1))).astype(np.float32)
     qa, qb = q.copy(), q.copy()
     qa[:, 0], qb[:, 0] = -5e-5, 5e-5
     fa, fb = field.evaluate_f(t(qa)).value, field.evaluate_f(t(qb)).value
-    wa, wb = whole.evaluate_f(t(qa)).value, whole.evaluate_f(t(qb)).value
     scale = float(whole.evaluate_f(t(q * 1.03)).value.abs().median())
-    assert float((fa - fb).abs().max()) <= float((wa - wb).abs().max()) + 0.02 * max(scale, 1e-6)
-    assert float((fa - wa).abs().median()) < 0.05 * max(scale, 1e-6)          # and the blend is the same function there
+    bound = torch.zeros_like(fa)
+    n_blend = torch.zeros_like(fa)
+    for k, fk in enumerate(field.fields):
+        wk = field._weights(t(qa), k)
+        jk = (fk.evaluate_f(t(qa)).value - fk.evaluate_f(t(qb)).value).abs()
+        bound = torch.maximum(bound, torch.where(wk > 0, jk, torch.zeros_like(jk)))
+        n_blend += (wk > 0).float()
+    assert float(n_blend.min()) >= 2                                           # every query sits in a cross-fade band
+    assert bool(((fa - fb).abs() <= bound + 0.01 * max(scale, 1e-6)).all())  # r2y: largest excess 3e-9, scale 0.073
+    # (the blend is NOT the un-chunked function value for value: a chunk's weights are normalised by ITS point counts,
+    # models/nksr_net.py:103-111, so the data-to-regulariser balance differs; the zero level sets agree -- checked above)
     # chunk_tmp_device = cpu: the solved chunks wait in host memory, visit the GPU per evaluation, return to the host
     rec.chunk_tmp_device = torch.device("cpu")
     parked = rec.reconstruct(t(xyz), t(nrm), detail_level=None, chunk_size=4.0, solver_tol=1e-5)
     assert all(f_.svh.device.type == "cpu" and f_.alpha.device.type == "cpu" for f_ in parked.fields)
     mp = parked.extract_dual_mesh(mise_iter=1)
     assert all(f_.svh.device.type == "cpu" for f_ in parked.fields)
-    assert torch.equal(mp.f, mesh.f) and torch.allclose(mp.v, mesh.v, atol=1e-6)
+    # same faces; the vertices move by the run-to-run difference of two solves to tol = 1e-5 (r2y: 4e-5 = 4e-4 voxels)
+    assert torch.equal(mp.f, mesh.f) and torch.allclose(mp.v, mesh.v, atol=1e-3)

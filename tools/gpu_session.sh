@@ -106,7 +106,7 @@ if has y1; then
   timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; tail -1 gpurun_out/${TAG}_smoke.log
   (timeout 300 python -m pytest tests/test_gpu_network.py -m gpu -q --tb=short --timeout 120 -p no:cacheprovider -k "tcgen05" 2>&1 | tail -40) > gpurun_out/${TAG}_pytest_tcgen05.log 2>&1
   tail -3 gpurun_out/${TAG}_pytest_tcgen05.log
-  timeout 400 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+  timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
   tail -c 700 gpurun_out/${TAG}_bench.json
   timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-mesh --backbone unet-tc > gpurun_out/${TAG}_bench_unet_tc.json 2> gpurun_out/${TAG}_bench_unet_tc.err
   python - <<PY
@@ -116,5 +116,29 @@ try:
     print("unet-tc", d["ms_per_step"], d["solve"]["stages_ms_timed_steps"])
 except Exception as e:
     print("no unet-tc line", e); print(open("gpurun_out/${TAG}_bench_unet_tc.err").read()[-800:])
+PY
+fi
+if has y2; then
+  timeout 200 python tools/chunk_diag.py > gpurun_out/${TAG}_chunk_diag.log 2>&1; tail -2 gpurun_out/${TAG}_chunk_diag.log | cut -c1-900
+  (timeout 200 python -m pytest tests/test_gpu_pipeline.py -m gpu -q --tb=short --timeout 150 -p no:cacheprovider -k "chunked" 2>&1 | tail -25) > gpurun_out/${TAG}_pytest_chunk.log 2>&1
+  tail -3 gpurun_out/${TAG}_pytest_chunk.log
+  timeout 240 python tools/tc_diag.py ${TAG} > gpurun_out/${TAG}_tc_diag_tn64.log 2>&1; grep -E "time_|unet_" gpurun_out/${TAG}_tc_diag_tn64.log | cut -c1-420
+  NKSR_TC_TN=128 timeout 240 python tools/tc_diag.py ${TAG} > gpurun_out/${TAG}_tc_diag_tn128.log 2>&1; grep -E "time_|unet_|random27" gpurun_out/${TAG}_tc_diag_tn128.log | cut -c1-420
+  NKSR_TC_UNET=0 timeout 240 ncu --set full --import-source on --clock-control none -k regex:"k_gather_gemm_t" --launch-skip 79 -c 9 -o /tmp/${TAG}_tc python tools/tc_diag.py ${TAG}ncu > gpurun_out/${TAG}_tc_ncu.log 2>&1
+  ncu -i /tmp/${TAG}_tc.ncu-rep --page raw --csv > gpurun_out/${TAG}_tc_ncu_raw.csv 2>/dev/null
+  ls -la gpurun_out | tail -12
+fi
+if has y3; then
+  (time timeout 420 python -m pytest tests -m gpu -q --tb=short --timeout 200 -p no:cacheprovider 2>&1 | tail -40) > gpurun_out/${TAG}_pytest_final.log 2>&1
+  tail -4 gpurun_out/${TAG}_pytest_final.log
+  timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke_final.log 2>&1; tail -1 gpurun_out/${TAG}_smoke_final.log
+  timeout 150 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-mesh --backbone unet-tc > gpurun_out/${TAG}_bench_unet_tc2.json 2> gpurun_out/${TAG}_bench_unet_tc2.err
+  python - <<PY
+import json
+try:
+    d=[json.loads(l) for l in open("gpurun_out/${TAG}_bench_unet_tc2.json") if l.startswith("{")][-1]
+    print("unet-tc", d["ms_per_step"], d["solve"]["stages_ms_timed_steps"])
+except Exception as e:
+    print("no unet-tc line", e); print(open("gpurun_out/${TAG}_bench_unet_tc2.err").read()[-800:])
 PY
 fi

@@ -66,31 +66,77 @@ def main():
         res = torch.randn((1000, c_out), generator=g).to(dev)
         ref = gather_gemm(x, idx, w3, b, res, True, impl="torch")
         record(f"random27_{c_in}x{c_out}", tc(x, idx, w3, b, res, True), ref)
-    # timing of one level-0-sized convolution against the mma.sync kernel
-    n = 2_000_000
-    x = torch.randn((n, 32), device=dev)
-    nb = (torch.arange(n, device=dev)[:, None] + torch.arange(-13, 14, device=dev)[None, :] * 37)
-    idx = torch.where((nb >= 0) & (nb < n), nb, torch.full_like(nb, -1)).to(torch.int32).contiguous()
-    w = torch.randn((27, 32, 32), device=dev) / 30
-    wt, wr = round_tf32(w).transpose(1, 2).contiguous(), round_tf32(w)
-    for name, fn in [("mma_sync_tf32", lambda: gather_gemm(x, idx, wr, None, None, True, tf32=2)),
-                     ("tcgen05_tf32", lambda: gather_gemm(x, idx, wt, None, None, True, tf32=3)),
-                     ("ffma_fp32", lambda: gather_gemm(x, idx, w, None, None, True, tf32=0))]:
+    # timing at the U-Net's layer shapes (rows scaled to the cfg4 hierarchy's level sizes / 8) against the mma.sync kernel
+    def ms_of(fn, reps=5):
         for _ in range(2):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(5):
+        for _ in range(reps):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        rec = dict(case=f"time_{name}", n_out=n, c=32, ms=ms, tflops=2 * n * 27 * 32 * 32 / ms / 1e9)
+        return e0.elapsed_time(e1) / reps
+
+    for n, c_in, c_out in [(2_000_000, 32, 32), (2_000_000, 64, 32), (425_000, 64, 64), (425_000, 128, 64),
+                           (100_000, 128, 128), (100_000, 256, 128), (25_000, 256, 256)]:
+        x = torch.randn((n, c_in), device=dev)
+        nb = (torch.arange(n, device=dev)[:, None] + torch.arange(-13, 14, device=dev)[None, :] * 37)
+        idx = torch.where((nb >= 0) & (nb < n), nb, torch.full_like(nb, -1)).to(torch.int32).contiguous()
+        w = torch.randn((27, c_in, c_out), device=dev) / (27 * c_in) ** 0.5
+        wt, wr = round_tf32(w).transpose(1, 2).contiguous(), round_tf32(w)
+        t_mma = ms_of(lambda: gather_gemm(x, idx, wr, None, None, True, tf32=2))
+        t_tc = ms_of(lambda: gather_gemm(x, idx, wt, None, None, True, tf32=3))
+        fl = 2 * n * 27 * c_in * c_out / 1e9
+        a, b_ = gather_gemm(x, idx, wr, None, None, True, tf32=2), gather_gemm(x, idx, wt, None, None, True, tf32=3)
+        rec = dict(case=f"time_{n}_{c_in}x{c_out}", ms_mma_sync=t_mma,
+                   ms_tcgen05=t_tc, tflops_mma_sync=fl / t_mma, tflops_tcgen05=fl / t_tc,
+                   gather_tb_s_tcgen05=n * 27 * c_in * 4 * max(1, c_out // (128 if c_out % 128 == 0 else 64)) / t_tc / 1e9,
+                   rel_diff=float((a - b_).abs().max() / a.abs().max()))
         out.append(rec)
         print(json.dumps(rec), flush=True)
-    a, b_ = gather_gemm(x, idx, wr, None, None, True, tf32=2), gather_gemm(x, idx, wt, None, None, True, tf32=3)
-    record("big_tc_vs_mma_sync", b_, a)
+        del x, nb, idx, a, b_
+    # where the U-Net backbone's time goes: the convolutions (our kernel) against the torch glue around them
+    if os.environ.get("NKSR_TC_UNET", "1") == "1":
+        import numpy as np
+        import nksr_b200.unet as U
+        from nksr_b200.network import NKSRNetwork
+        from nksr_b200.svh import SparseFeatureHierarchy
+        from tests import scenes
+        xyz, _, _ = scenes.crop("cfg4_outdoor", 1_000_000, with_sensor=True)
+        pts = torch.from_numpy(np.ascontiguousarray(xyz)).to(dev)
+        svh = SparseFeatureHierarchy(0.1, 4, dev).build_point_splatting(pts)
+        net = NKSRNetwork(dict(backbone="unet", tree_depth=4, kernel_dim=4, precision="tc")).to(dev)
+        feat = torch.nn.functional.normalize(torch.randn((pts.shape[0], 3), device=dev), dim=1)
+        acc = {"ms": 0.0, "calls": 0, "ev": []}
+        orig = U.gather_gemm
+
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig(*a, **k)
+            e1.record()
+            acc["ev"].append((e0, e1))
+            return r
+        with torch.no_grad():
+            enc = net.encoder(pts, feat, svh, 0)
+            for mode in (3, True):
+                net.backbone_net(enc.x0, svh, tf32=mode)
+                total = ms_of(lambda: net.backbone_net(enc.x0, svh, tf32=mode), reps=3)
+                U.gather_gemm = timed
+                acc["ev"].clear()
+                net.backbone_net(enc.x0, svh, tf32=mode)
+                torch.cuda.synchronize()
+                U.gather_gemm = orig
+                conv = sum(a.elapsed_time(b) for a, b in acc["ev"])
+                t_enc = ms_of(lambda: net.encoder(pts, feat, svh, 0), reps=3)
+                rec = dict(case="unet_breakdown", mode="tcgen05" if mode == 3 else "mma_sync",
+                           voxels=[svh.num_voxels(l) for l in range(4)],
+                           backbone_ms=total, conv_ms=conv, conv_calls=len(acc["ev"]), glue_ms=total - conv,
+                           point_encoder_ms=t_enc)
+                out.append(rec)
+                print(json.dumps(rec), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/{tag}_tc_diag.json", "w") as f:
         json.dump(out, f, indent=1)
