@@ -142,3 +142,10 @@ except Exception as e:
     print("no unet-tc line", e); print(open("gpurun_out/${TAG}_bench_unet_tc2.err").read()[-800:])
 PY
 fi
+if has y4; then
+  NKSR_TC_QUICK=1 timeout 70 python tools/tc_diag.py ${TAG}q > gpurun_out/${TAG}_tc_quick.log 2>&1; grep -E "time_|unet_" gpurun_out/${TAG}_tc_quick.log | cut -c1-400
+  NKSR_TC_QUICK=1 NKSR_TC_UNET=0 timeout 60 ncu --set full --import-source on --clock-control none -k regex:"k_gather_gemm_tc" --launch-skip 2 -c 2 -o /tmp/${TAG}_tc128 python tools/tc_diag.py ${TAG}ncu2 > gpurun_out/${TAG}_tc128_ncu.log 2>&1
+  ncu -i /tmp/${TAG}_tc128.ncu-rep --page raw --csv > gpurun_out/${TAG}_tc128_ncu_raw.csv 2>/dev/null
+  ncu -i /tmp/${TAG}_tc128.ncu-rep --page source --csv --print-source sass > /tmp/${TAG}_tc128_source.csv 2>/dev/null
+  python tools/hot_lines.py /tmp/${TAG}_tc128_source.csv > gpurun_out/${TAG}_tc128_hot_sass.txt 2>&1
+fi

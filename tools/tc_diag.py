@@ -36,7 +36,8 @@ def main():
         out.append(rec)
         print(json.dumps(rec), flush=True)
 
-    for c_in, c_out in [(32, 32), (32, 64), (64, 64), (128, 64), (32, 96)]:
+    quick = os.environ.get("NKSR_TC_QUICK") == "1"          # only the wide-layer timing (+ the U-Net breakdown)
+    for c_in, c_out in ([] if quick else [(32, 32), (32, 64), (64, 64), (128, 64), (32, 96)]):
         n = 300
         x = torch.randn((n, c_in), generator=g).to(dev)
         ident = torch.arange(n, dtype=torch.int32, device=dev)[:, None].contiguous()
@@ -79,7 +80,7 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    for n, c_in, c_out in [(2_000_000, 32, 32), (2_000_000, 64, 32), (425_000, 64, 64), (425_000, 128, 64),
+    for n, c_in, c_out in [(100_000, 128, 128)] if quick else [(2_000_000, 32, 32), (2_000_000, 64, 32), (425_000, 64, 64), (425_000, 128, 64),
                            (100_000, 128, 128), (100_000, 256, 128), (25_000, 256, 256)]:
         x = torch.randn((n, c_in), device=dev)
         nb = (torch.arange(n, device=dev)[:, None] + torch.arange(-13, 14, device=dev)[None, :] * 37)
