@@ -52,6 +52,8 @@ def lib():
         L.nksr_cpu_structural_counts.argtypes = [C.c_void_p, C.c_void_p]
         L.nksr_cpu_structural_row.restype = C.c_int64
         L.nksr_cpu_structural_row.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.nksr_cpu_nbr27.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.nksr_cpu_pool27.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -80,6 +82,20 @@ class CpuSvh:
         q = np.ascontiguousarray(xyz, np.float32)
         out = np.empty((self.depth, q.shape[0]), np.int32)
         lib().nksr_cpu_locate(self.h, _p(q), q.shape[0], _p(out))
+        return out
+
+    def nbr27(self, l):
+        """(n_l, 27) int32 neighbour table, -1 = inactive (slot order of nksr_oracle._OFF27)"""
+        out = np.empty((self.n(l), 27), np.int32)
+        lib().nksr_cpu_nbr27(self.h, int(l), _p(out))
+        return out
+
+    def pool27(self, l, acc):
+        """sum of `acc` (n_l, C) float64 over the 27-neighbourhood of every voxel, slots added in table order"""
+        acc = np.ascontiguousarray(acc, np.float64)
+        nb = self.nbr27(l)
+        out = np.empty_like(acc)
+        lib().nksr_cpu_pool27(_p(nb), acc.shape[0], _p(acc), acc.shape[1], _p(out))
         return out
 
     def structural_counts(self):

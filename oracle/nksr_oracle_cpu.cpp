@@ -436,6 +436,43 @@ void nksr_cpu_locate(void* h, const float* xyz, int64_t m, int32_t* base) {
   }
 }
 
+// 27-neighbour table of level l: out[i*27 + s], s = (dx+1)*9 + (dy+1)*3 + (dz+1), -1 where the neighbour is inactive
+// (the table the stand-in network's smoothing and the CPU baseline read; one binary search per entry)
+void nksr_cpu_nbr27(void* h, int l, int32_t* out) {
+  const Svh& s = *static_cast<Svh*>(h);
+  const int64_t n = (int64_t)s.keys[l].size();
+  const int lim = 1 << 21;      // 21 bits per axis in a key (KEY_BITS of the numpy restatement)
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    int x, y, z;
+    demorton3(s.keys[l][i], x, y, z);
+    int t = 0;
+    for (int dx = -1; dx <= 1; ++dx)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dz = -1; dz <= 1; ++dz, ++t) {
+          const int a = x + dx, b = y + dy, c = z + dz;
+          const bool ok = a >= 0 && b >= 0 && c >= 0 && a < lim && b < lim && c < lim;
+          out[i * 27 + t] = ok ? s.find(l, morton3(a, b, c)) : -1;
+        }
+  }
+}
+
+// out[i][c] = sum over the slots s = 0..26 (in this order, fp64) of acc[nbr27[i][s]][c]: the 27-neighbourhood pooling of
+// the stand-in network (nksr_b200/network.py, csrc: nksr_pool27), with the summation order of the numpy restatement
+void nksr_cpu_pool27(const int32_t* nbr27, int64_t n, const double* acc, int C, double* out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    double* o = out + i * C;
+    for (int c = 0; c < C; ++c) o[c] = 0.0;
+    for (int t = 0; t < 27; ++t) {
+      const int j = nbr27[i * 27 + t];
+      if (j < 0) continue;
+      const double* a = acc + (int64_t)j * C;
+      for (int c = 0; c < C; ++c) o[c] += a[c];
+    }
+  }
+}
+
 // SPEC S6 storage pattern, restated independently of the numpy oracle: row (l,i) stores every ACTIVE column in
 // the same-level 5^3 stencil, in the box [((u-1)>>k)-1, ((u+1)>>k)+1]^3 of every coarser level l+k, and the
 // transposes of the latter.  cnt[row] = stored entries of the row (own + transposed).

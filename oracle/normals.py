@@ -26,21 +26,38 @@ def knn_indices(xyz: np.ndarray, k: int, workers: int = -1):
     return idx.reshape(xyz.shape[0], -1), d.reshape(xyz.shape[0], -1)
 
 
-def pca_normals(xyz: np.ndarray, idx: np.ndarray):
-    """unit eigenvector of the smallest eigenvalue of the neighbourhood covariance (float64);
-    also returns the eigenvalues (ascending) so that tests can skip degenerate neighbourhoods."""
-    p = np.asarray(xyz, np.float64)[idx]                         # (N,k,3)
+def _pca_block(p64, idx):
+    p = p64[idx]                                                 # (n,k,3)
     c = p - p.mean(axis=1, keepdims=True)
     cov = np.einsum('nki,nkj->nij', c, c) / idx.shape[1]
     w, v = np.linalg.eigh(cov)
     return v[:, :, 0], w
 
 
+def pca_normals(xyz: np.ndarray, idx: np.ndarray, workers: int = -1):
+    """unit eigenvector of the smallest eigenvalue of the neighbourhood covariance (float64);
+    also returns the eigenvalues (ascending) so that tests can skip degenerate neighbourhoods.
+    Points are independent, so blocks of them go to a thread pool (numpy releases the GIL in the gathers, einsum and
+    eigh): the same arithmetic per point whatever the block size, on all host cores like the kNN search."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    p64 = np.asarray(xyz, np.float64)
+    n = idx.shape[0]
+    nw = (os.cpu_count() or 1) if workers is None or workers < 0 else max(1, int(workers))
+    block = 16384
+    if nw == 1 or n <= block:
+        return _pca_block(p64, idx)
+    spans = [(s, min(s + block, n)) for s in range(0, n, block)]
+    with ThreadPoolExecutor(max_workers=nw) as ex:
+        parts = list(ex.map(lambda ab: _pca_block(p64, idx[ab[0]:ab[1]]), spans))
+    return np.concatenate([q[0] for q in parts]), np.concatenate([q[1] for q in parts])
+
+
 def estimate_normal_preprocess(xyz: np.ndarray, sensor: np.ndarray, knn: int = 64, max_angle_deg: float = 85.0,
                                workers: int = -1):
     """Returns xyz', normal' (float32) of the kept points, the keep mask, and (normals of ALL points, cos, eigvals)."""
     idx, _ = knn_indices(xyz, min(knn, xyz.shape[0]), workers)
-    n, ev = pca_normals(xyz, idx)
+    n, ev = pca_normals(xyz, idx, workers)
     view = np.asarray(sensor, np.float64) - np.asarray(xyz, np.float64)
     view = view / (np.linalg.norm(view, axis=-1, keepdims=True) + 1e-6)
     cos = np.sum(view * n, axis=1)

@@ -25,15 +25,23 @@ from . import cpu_port as P
 from . import nksr_oracle as O
 
 
+def _scatter_sum(index, values, n):
+    """out[j] = sum of values[i] over index[i] == j, added in the order of i (what np.add.at does, one bincount per
+    column: the same fp64 additions in the same order, without np.add.at's per-element dispatch)"""
+    return np.stack([np.bincount(index, weights=values[:, c], minlength=n) for c in range(values.shape[1])], axis=1)
+
+
 def _children_sum(keys_fine, keys_coarse, acc_fine):
     """sum of the (<= 8) children of every coarse voxel (parent key = child key >> 3)."""
     par = np.searchsorted(keys_coarse, keys_fine >> 3)
-    out = np.zeros((keys_coarse.shape[0], acc_fine.shape[1]), np.float64)
-    np.add.at(out, par, acc_fine)
-    return out
+    return _scatter_sum(par, acc_fine, keys_coarse.shape[0])
 
 
-def _pool27(osvh, l, acc):
+def _pool27(osvh, l, acc, svh_cpp=None):
+    """sum over the 27-neighbourhood, slots added in table order.  With the C++ hierarchy at hand the table and the sum
+    come from it (OpenMP; tests/test_cpu_port.py holds the two bitwise equal), else from the numpy restatement."""
+    if svh_cpp is not None:
+        return svh_cpp.pool27(l, acc)
     nb = osvh.nbr27(l)                                   # (n,27) index or -1
     out = np.zeros_like(acc)
     for s in range(27):
@@ -53,12 +61,11 @@ def standin_features(osvh, svh_cpp, xyz, point_feat, network):
     pooled, acc = [], None
     for l in range(L):
         if l == 0:
-            acc = np.zeros((osvh.n(0), 4), np.float64)
             ok = base0 >= 0
-            np.add.at(acc, base0[ok], src[ok])
+            acc = _scatter_sum(base0[ok], src[ok], osvh.n(0))
         else:
             acc = _children_sum(osvh.keys[l - 1], osvh.keys[l], acc)
-        pooled.append(_pool27(osvh, l, acc))
+        pooled.append(_pool27(osvh, l, acc, svh_cpp))
     C = network.kernel_dim
     basis, normal, up = {}, {}, None
     for l in range(L - 1, -1, -1):
