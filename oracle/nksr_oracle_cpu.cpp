@@ -14,6 +14,7 @@
 // Build (oracle/Makefile):  g++ -O2 -fopenmp -shared -fPIC -o oracle/_build/libnksr_oracle_cpu.so oracle/nksr_oracle_cpu.cpp
 // (no -ffast-math: the voxel quantisation relies on IEEE fp32 division.)
 #include <algorithm>
+#include <parallel/algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -174,7 +175,7 @@ void* nksr_cpu_svh_build(const float* xyz, int64_t n, float voxel_size, int dept
       const int bx = ((h[0] >> l) - 1) >> 1, by = ((h[1] >> l) - 1) >> 1, bz = ((h[2] >> l) - 1) >> 1;
       for (int a = 0; a < 8; ++a) k[(size_t)i * 8 + a] = morton3(bx + ((a >> 2) & 1), by + ((a >> 1) & 1), bz + (a & 1));
     }
-    std::sort(k.begin(), k.end());
+    __gnu_parallel::sort(k.begin(), k.end());      // OpenMP multiway mergesort of libstdc++'s parallel mode
     k.erase(std::unique(k.begin(), k.end()), k.end());
   }
   s->offset.assign(depth + 1, 0);
