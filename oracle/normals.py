@@ -44,7 +44,7 @@ def pca_normals(xyz: np.ndarray, idx: np.ndarray, workers: int = -1):
     p64 = np.asarray(xyz, np.float64)
     n = idx.shape[0]
     nw = (os.cpu_count() or 1) if workers is None or workers < 0 else max(1, int(workers))
-    block = 16384
+    block = 8192                                                 # ~40 MB of temporaries per worker
     if nw == 1 or n <= block:
         return _pca_block(p64, idx)
     spans = [(s, min(s + block, n)) for s in range(0, n, block)]
