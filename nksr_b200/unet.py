@@ -21,6 +21,7 @@ tests compare the kernel with (tests/test_gpu_network.py).
 from __future__ import annotations
 
 import math
+import weakref
 from types import SimpleNamespace
 
 import torch
@@ -165,9 +166,11 @@ def up_table(svh, l):
     derived from)."""
     child8, parent = svh.child8[l + 1], svh.parent[l]
     cache = svh.__dict__.setdefault("_unet_up_tables", {})
-    key = (child8.data_ptr(), parent.data_ptr(), str(parent.device))
     hit = cache.get(l)
-    if hit is None or hit[0] != key:
+    # valid while the very tensor objects it was derived from are the hierarchy's tables (a rebuilt or moved hierarchy
+    # holds new ones; weak references, so a recycled address or id cannot pass for the old table)
+    if hit is None or hit[0][0]() is not child8 or hit[0][1]() is not parent:
+        key = (weakref.ref(child8), weakref.ref(parent))
         n_l = svh.num_voxels(l)
         octant = octant_of_children(child8, n_l)
         rows = torch.nonzero((octant >= 0) & (parent >= 0)).squeeze(1)
